@@ -1,0 +1,63 @@
+"""ORACLE fixture generator — run in the build container only (needs /root/reference).
+
+    python -m oracle.make_goldens
+
+Runs the UNMODIFIED reference ``modules.TrackingNet`` (imported in place, shimmed per SURVEY
+F3) on seeded synthetic frame-pairs with seeded synthetic weights and stores inputs' seeds +
+the reference outputs under tests/golden/.  Weights/inputs are regenerated from seeds by
+``mmmot_b200.synthetic`` at test time (an 85 MB state_dict cannot be committed), so a fixture
+is ~10-100 KB.  The reference ships no golden vectors of its own — these are them.
+"""
+import os
+
+import torch
+
+from mmmot_b200.synthetic import synthetic_pair, synthetic_state_dict
+from oracle import ref_loader
+
+# (name, fusion, affinity_op, softmax_mode, neg_threshold, N, M, pts, hw, ragged, seed)
+CASES = [
+    ("mul_A_n8", "A", "multiply", "none", 0.2, 8, 8, 32, 32, False, 1),
+    ("mul_B_n6x9", "B", "multiply", "none", 0.2, 6, 9, 24, 32, True, 2),
+    ("mul_C_n8", "C", "multiply", "none", 0.2, 8, 8, 32, 32, False, 3),
+    ("subabs_dualadd_C_n8", "C", "minus_abs", "dual_add", 0.2, 8, 8, 32, 32, True, 4),
+    ("rrc_subabs_dualadd_C_n5x3", "C", "minus_abs", "dual_add", 0.0, 5, 3, 16, 64, True, 5),
+    ("single_C_n4", "C", "minus", "single", 0.2, 4, 4, 16, 32, False, 6),
+    ("dual_B_n1x2", "B", "multiply", "dual", 0.2, 1, 2, 16, 32, True, 7),
+    ("dualmax_A_n3x7", "A", "minus_abs", "dual_max", 0.2, 3, 7, 20, 32, True, 8),
+]
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def reference_forward(case, want_feats=False):
+    name, fusion, op, sm, thr, n, m, pts, hw, ragged, seed = case
+    net = ref_loader.load_tracking_net(
+        seq_len=2, score_arch="branch_cls", appear_arch="vgg", appear_len=512,
+        appear_skippool=True, appear_fpn=False, point_arch="v1", point_len=512,
+        without_reflectivity=True, softmax_mode=sm, affinity_op=op, end_arch="v2",
+        end_mode="avg", test_mode=2, score_fusion_arch=fusion, neg_threshold=thr,
+        dropblock=0, use_dropout=False)
+    sd = synthetic_state_dict(fusion, seed=seed)
+    net.load_state_dict(sd, strict=True)          # also pins the key/shape schema
+    dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
+    with torch.no_grad():
+        feats, _ = net.feature(dets, info)
+        det, link, new, end, trans = net(dets, info, split)
+    return {"det": det, "link": link[0], "new": new, "end": end,
+            "trans1": trans[0], "trans2": trans[1], "feats": feats}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    for case in CASES:
+        out = reference_forward(case)
+        out = {k: v.clone().contiguous() for k, v in out.items()}
+        out["case"] = case
+        torch.save(out, os.path.join(OUT, case[0] + ".pt"))
+        print(case[0], {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")})
+
+
+if __name__ == "__main__":
+    main()
