@@ -1,0 +1,170 @@
+/*
+ * mmmot_b200.h — C ABI of libmmmot_sm100a.so
+ *
+ * B200-native (sm_100a) implementation of mmMOT's per-frame-pair association forward.
+ * The reference (ZwwWayne/mmMOT) has no FFI of its own: its boundary is the Python class
+ * modules/tracking_net.py:15 `TrackingNet` and the function solvers.py:9 `ortools_solve`.
+ * Each entry point below replaces one group of ATen/OR-tools calls behind that boundary; the
+ * reference lines replaced are cited per function.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless marked host.
+ *   - no allocation, no ownership transfer, stateless, stream-ordered (last argument is a
+ *     cudaStream_t passed as void*), thread-safe across streams.
+ *   - return 0 on success, a negative MMMOT_E_* on a bad argument, or a positive cudaError_t.
+ *   - all real data is fp32; `stats` scratch is fp64.
+ *   - "group" = one GroupNorm domain.  A frame-pair with N previous / M next detections has
+ *     L = N + M detections; all pairs of one call share N, M, crop size H x W.
+ *   - feature tensors are channel-major: feats[pair][stack 0..2][512][L]
+ *     (stack 0 = image, 1 = LiDAR, 2 = fused; reference: modules/tracking_net.py:40,131-145).
+ */
+#ifndef MMMOT_B200_H
+#define MMMOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMMOT_ABI_VERSION 1
+
+enum {
+  MMMOT_E_ARG = -1,        /* null pointer / non-positive size / unsupported enum */
+  MMMOT_E_WORKSPACE = -2,  /* workspace too small */
+  MMMOT_E_SHAPE = -3       /* shape constraint violated (see function comment) */
+};
+
+/* fusion_module_{A,B,C}: reference modules/fusion_net.py:73,45,6 */
+enum { MMMOT_FUSION_A = 0, MMMOT_FUSION_B = 1, MMMOT_FUSION_C = 2 };
+/* batch_multiply / batch_minus_abs / batch_minus: reference modules/gcn.py:6,17,32 */
+enum { MMMOT_AFF_MULTIPLY = 0, MMMOT_AFF_MINUS_ABS = 1, MMMOT_AFF_MINUS = 2 };
+/* softmax_mode: reference modules/tracking_net.py:109-124 */
+enum { MMMOT_SM_NONE = 0, MMMOT_SM_SINGLE = 1, MMMOT_SM_DUAL = 2, MMMOT_SM_DUAL_ADD = 3, MMMOT_SM_DUAL_MAX = 4 };
+
+/*
+ * Prepared weights.  Produced once per checkpoint by the host (mmmot_b200/weights.py) from the
+ * reference state_dict: eval-mode BatchNorm folded into the preceding conv, the two constant
+ * STN transforms folded into the PointNet convs they feed, every matrix stored
+ * TRANSPOSED as Wt[K][Cout] (K-major rows, Cout contiguous).
+ */
+enum mmmot_weight_id {
+  /* VGG16-BN trunk, 13 convs: Wt[(ky*3+kx)*Cin + ci][Cout], bias[Cout]  (appear_net.py:166-172) */
+  MMMOT_W_VGG_WT0 = 0,            /* .. +12 */
+  MMMOT_W_VGG_B0 = 13,            /* .. +12 */
+  /* SkipPool heads s=0..3, 10 tensors each (appear_net.py:18-32):
+     +0 gn0_w[C] +1 gn0_b[C] +2 w1t[C][mid] +3 b1[mid] +4 gn1_w +5 gn1_b +6 w2t[mid][128] +7 b2 +8 gn2_w +9 gn2_b */
+  MMMOT_W_SKIP0 = 26,             /* .. +39 */
+  /* PointNet trunk (point_net.py:115-138), layer i=1..5: +0 wt[Cin][Cout] +1 b +2 gn_w +3 gn_b */
+  MMMOT_W_PN_L1 = 66,             /* .. 5 layers x 4 = 20 */
+  /* PointNet head (point_net.py:25-41) */
+  MMMOT_W_PN_WHAT = 86,           /* [64][512]   local-feature part of conv1, T2 folded in   */
+  MMMOT_W_PN_WHGT = 87,           /* [1024][512] global-feature part of conv1                */
+  MMMOT_W_PN_BH = 88, MMMOT_W_PN_GHW = 89, MMMOT_W_PN_GHB = 90,
+  MMMOT_W_PN_WOT = 91,            /* [512][512] conv2 */
+  MMMOT_W_PN_BO = 92, MMMOT_W_PN_GOW = 93, MMMOT_W_PN_GOB = 94,
+  /* fusion (fusion_net.py): A uses WPT as the [1024][512] matrix; B uses WPT/WIT; C adds gates */
+  MMMOT_W_FU_WPT = 95, MMMOT_W_FU_BP = 96, MMMOT_W_FU_GPW = 97, MMMOT_W_FU_GPB = 98,
+  MMMOT_W_FU_WIT = 99, MMMOT_W_FU_BI = 100, MMMOT_W_FU_GIW = 101, MMMOT_W_FU_GIB = 102,
+  MMMOT_W_FU_GATE_PT = 103, MMMOT_W_FU_GATE_PB = 104, MMMOT_W_FU_GATE_IT = 105, MMMOT_W_FU_GATE_IB = 106,
+  /* w_det (tracking_net.py:92-100), BN folded */
+  MMMOT_W_WD_W1T = 107, MMMOT_W_WD_B1 = 108, MMMOT_W_WD_W2T = 109, MMMOT_W_WD_B2 = 110,
+  MMMOT_W_WD_W3 = 111, MMMOT_W_WD_B3 = 112,
+  /* affinity (gcn.py:59-66) + new/end conv0 (new_end.py:48-52) stacked as one [512][1024] matrix */
+  MMMOT_W_AF_W01T = 113, MMMOT_W_AF_B01 = 114,
+  MMMOT_W_AF_G1W = 115, MMMOT_W_AF_G1B = 116,   /* conv1.1  GN(512,512) */
+  MMMOT_W_AF_G0W = 117, MMMOT_W_AF_G0B = 118,   /* w_new_end.conv0.1  GN(1,512) */
+  MMMOT_W_AF_W2T = 119, MMMOT_W_AF_B2 = 120, MMMOT_W_AF_G2W = 121, MMMOT_W_AF_G2B = 122,
+  MMMOT_W_AF_W3T = 123, MMMOT_W_AF_B3 = 124, MMMOT_W_AF_G3W = 125, MMMOT_W_AF_G3B = 126,
+  MMMOT_W_AF_W4 = 127, MMMOT_W_AF_B4 = 128,
+  /* new/end 1-D MLP (new_end.py:53-60) */
+  MMMOT_W_NE_W1T = 129, MMMOT_W_NE_B1 = 130, MMMOT_W_NE_G1W = 131, MMMOT_W_NE_G1B = 132,
+  MMMOT_W_NE_W2T = 133, MMMOT_W_NE_B2 = 134, MMMOT_W_NE_G2W = 135, MMMOT_W_NE_G2B = 136,
+  MMMOT_W_NE_W3 = 137, MMMOT_W_NE_B3 = 138,
+  MMMOT_W_COUNT = 139
+};
+
+typedef struct mmmot_weights {
+  const float* w[MMMOT_W_COUNT];
+} mmmot_weights;
+
+int mmmot_abi_version(void);
+/* number of SMs / name of the current device: lets the host fail loudly when no sm_100 GPU is present */
+int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Appearance: VGG16-BN trunk + 4 SkipPool heads -> stack 0 of feats.
+ * Replaces AppearanceNet.forward, reference modules/appear_net.py:166-190 (+ vgg.py:67-80).
+ *   crops  [n_img][3][H][W]   (H, W multiples of 32), n_img = pairs*L
+ *   feats  [pairs][3][512][L] ; writes feats[p][0][:][l] for image p*L + l
+ * workspace: mmmot_appearance_workspace(n_img, H, W) bytes.
+ */
+size_t mmmot_appearance_workspace(int n_img, int H, int W);
+int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops, int n_img, int H, int W,
+                         int L, float* feats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointNet encoder over ragged per-detection point sets -> stack 1 of feats.
+ * Replaces PointNet_v1.forward, reference modules/point_net.py:25-44,115-153.
+ *   points     [P_total][3]  xyz, detections concatenated in order
+ *   det_split  [pairs*L + 1] int32 CSR offsets into points (device)
+ *   h_det_split same array on the HOST (used only to size the launch; the reference reads it
+ *               with .item() per detection, point_net.py:33-35,140-142)
+ * Every pair is one GroupNorm domain (all points of its L detections).
+ */
+size_t mmmot_pointnet_workspace(int pairs, int L, long p_total);
+int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points, const int* det_split,
+                       const int* h_det_split, int pairs, int L, float* feats,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fusion A/B/C -> stack 2 of feats, then the detection-score branch on all 3 stacks.
+ * Replaces fusion_module_{A,B,C}.forward (modules/fusion_net.py:31-42,62-70,85-92) and
+ * TrackingNet.determine_det eval branch (modules/tracking_net.py:149-163).
+ *   det_scores [pairs][3][L]   = sigmoid(w_det(feats)) - [. < neg_threshold]
+ */
+size_t mmmot_fusion_det_workspace(int pairs, int L);
+int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, float neg_threshold,
+                         int pairs, int L, float* feats, float* det_scores,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pairwise affinity + start/end indicator + softmax mode.
+ * Replaces affinity_module.forward (modules/gcn.py:68-82), NewEndIndicator_v2.forward
+ * (modules/new_end.py:62-82, mode 'avg') and TrackingNet.associate (tracking_net.py:106-126).
+ * The 3 x 512 x N x M pairwise tensor is generated tile by tile and never stored.
+ *   link  [pairs][3][N][M]
+ *   new_s [pairs][3][M]   end_s [pairs][3][N]   (un-padded; the host pads with zeros as
+ *                                                tracking_net.py:183-189 does)
+ */
+size_t mmmot_affinity_workspace(int pairs, int n, int m);
+int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode,
+                       int pairs, int n, int m, const float* feats,
+                       float* link, float* new_s, float* end_s,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Association integer programme for 2-frame pairs, solved exactly as a rectangular
+ * assignment problem.  Replaces ortools_solve, reference solvers.py:9-138.
+ *   det [pairs][L], link [pairs][N][M], new_s/end_s [pairs][L] (zero-padded like the reference's
+ *   forward output); strides in floats between consecutive pairs are given explicitly so the
+ *   solver can read the test_mode stack straight out of the forward outputs.
+ *   outputs (fp32 0/1, same layout as solvers.py:116-131):
+ *   a_det [pairs][L], a_link [pairs][N][M], a_new [pairs][L], a_end [pairs][L]
+ *   match [pairs][N] int32: column matched to previous detection j, or -1.
+ */
+size_t mmmot_lp_workspace(int pairs, int n, int m);
+int mmmot_lp_assign(const float* det, long det_stride, const float* link, long link_stride,
+                    const float* new_s, long new_stride, const float* end_s, long end_stride,
+                    int pairs, int n, int m,
+                    float* a_det, float* a_link, float* a_new, float* a_end, int* match,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* counts kernel launches made through this library since process start (bench.py gpu_launches) */
+unsigned long long mmmot_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMMOT_B200_H */

@@ -1,0 +1,278 @@
+// Pairwise affinity + start/end ("new"/"end") indicator + softmax mode.
+// Replaces reference modules/gcn.py:68-82 (affinity_module.forward), modules/new_end.py:62-82
+// (NewEndIndicator_v2.forward, mode 'avg') and modules/tracking_net.py:106-126 (associate).
+//
+// Groups g = pair*3 + stack.  The pairwise tensor x[g][c][i][j] (reference gcn.py:13,24-27;
+// 100.7 MB per pair at N=M=128) is generated inside the first contraction's operand loader and
+// never exists in HBM; affinity conv1.0 and new/end conv0 (both 512->512 on the same x) run as
+// ONE 512->1024 contraction.
+#include "gemm_simt.cuh"
+#include "norm_ops.cuh"
+
+namespace {
+
+// Row/column means of y = relu(GN_{1,512}(conv0 x)):  new_vec = mean_i y (per j), end_vec = mean_j y
+// (reference new_end.py:69-71).  One CTA per (g, c); V is channel-major over absolute columns:
+// V[c][g*(M+N) + j] (new part), V[c][g*(M+N) + M + i] (end part).
+__global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restrict__ y0, long y_gs,
+                                                          const float* __restrict__ sc,
+                                                          const float* __restrict__ sh, int N, int M,
+                                                          long ldv, float* __restrict__ V) {
+  extern __shared__ float colacc[];  // [M]
+  const int g = blockIdx.x / 512, c = blockIdx.x % 512;
+  const float a = sc[g * 512 + c], b = sh[g * 512 + c];
+  const float* src = y0 + (long)g * y_gs + (long)c * N * M;
+  float* vout = V + (long)c * ldv + (long)g * (M + N);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) colacc[j] = 0.f;
+  __syncthreads();
+  // each warp owns rows i = warp, warp+nw, ...; lanes stride the columns
+  for (int j0 = 0; j0 < M; j0 += 32) {
+    const int j = j0 + lane;
+    float cs = 0.f;
+    for (int i = warp; i < N; i += nw) {
+      if (j < M) cs += fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f);
+    }
+    if (j < M) atomicAdd(&colacc[j], cs);
+  }
+  for (int i = warp; i < N; i += nw) {
+    float rs = 0.f;
+    for (int j = lane; j < M; j += 32) rs += fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) vout[M + i] = rs / (float)M;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += blockDim.x) vout[j] = colacc[j] / (float)N;
+}
+
+// Tile table for the new/end MLP: group 2g = new columns (len M), 2g+1 = end columns (len N).
+__global__ void ne_tiles_kernel(int G, int N, int M, int tn, int tm_, int4* __restrict__ tiles,
+                                int* __restrict__ cnt) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = tm_ + tn;  // tiles per g: tm_ for the M new columns, tn for the N end columns
+  if (idx < G * 2) cnt[idx] = (idx & 1) ? N : M;
+  if (idx >= G * per) return;
+  int g = idx / per, t = idx - g * per;
+  if (t < tm_) tiles[idx] = make_int4(2 * g, g * (M + N) + t * 128, min(128, M - t * 128), 0);
+  else { t -= tm_; tiles[idx] = make_int4(2 * g + 1, g * (M + N) + M + t * 128, min(128, N - t * 128), 0); }
+}
+
+// out[col] = sigmoid(w3 . relu(GN(h2))[:, col] + b3) for the new/end MLP; scatters into new_s / end_s.
+__global__ void ne_final_kernel(const float* __restrict__ h2, long ldv, const float* __restrict__ sc,
+                                const float* __restrict__ sh, const float* __restrict__ w3,
+                                const float* __restrict__ b3, int G, int N, int M,
+                                float* __restrict__ new_s, float* __restrict__ end_s) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * (M + N)) return;
+  int g = idx / (M + N), r = idx - g * (M + N);
+  int grp = 2 * g + (r >= M);
+  float a = b3[0];
+  for (int c = 0; c < 128; c++)
+    a = fmaf(w3[c], fmaxf(fmaf(h2[(long)c * ldv + idx], sc[grp * 128 + c], sh[grp * 128 + c]), 0.f), a);
+  float s = mm_sigmoid(a);
+  if (r < M) new_s[(long)g * M + r] = s; else end_s[(long)g * N + (r - M)] = s;
+}
+
+// z[g][s] = w4 . relu(GN(y3[g]))[:, s] + b4      (reference gcn.py:65-66: last 1x1 conv 128 -> 1)
+__global__ void link_logit_kernel(const float* __restrict__ y3, const float* __restrict__ sc,
+                                  const float* __restrict__ sh, const float* __restrict__ w4,
+                                  const float* __restrict__ b4, int G, int NM, float* __restrict__ z) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)G * NM) return;
+  int g = (int)(idx / NM);
+  int s = (int)(idx - (long)g * NM);
+  const float* col = y3 + (long)g * 128 * NM + s;
+  float a = b4[0];
+#pragma unroll 8
+  for (int c = 0; c < 128; c++)
+    a = fmaf(__ldg(w4 + c), fmaxf(fmaf(col[(long)c * NM], __ldg(sc + g * 128 + c), __ldg(sh + g * 128 + c)), 0.f), a);
+  z[idx] = a;
+}
+
+// softmax statistics: rows (dim=-1, over j) and columns (dim=-2, over i); one warp per row/column.
+__global__ void softmax_stats_kernel(const float* __restrict__ z, int G, int N, int M,
+                                     float* __restrict__ rmax, float* __restrict__ rsum,
+                                     float* __restrict__ cmax, float* __restrict__ csum) {
+  long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= (long)G * (N + M)) return;
+  int g = (int)(w / (N + M)), r = (int)(w - (long)g * (N + M));
+  const float* base = z + (long)g * N * M;
+  int cntv, stride;
+  const float* p0;
+  if (r < N) { p0 = base + (long)r * M; cntv = M; stride = 1; }
+  else { p0 = base + (r - N); cntv = N; stride = M; }
+  float mx = -INFINITY;
+  for (int t = lane; t < cntv; t += 32) mx = fmaxf(mx, p0[(long)t * stride]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sm = 0.f;
+  for (int t = lane; t < cntv; t += 32) sm += expf(p0[(long)t * stride] - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  if (lane == 0) {
+    if (r < N) { rmax[g * N + r] = mx; rsum[g * N + r] = sm; }
+    else { cmax[g * M + r - N] = mx; csum[g * M + r - N] = sm; }
+  }
+}
+
+__global__ void softmax_apply_kernel(const float* __restrict__ z, int mode, int G, int N, int M,
+                                     const float* __restrict__ rmax, const float* __restrict__ rsum,
+                                     const float* __restrict__ cmax, const float* __restrict__ csum,
+                                     float* __restrict__ link) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)G * N * M) return;
+  int g = (int)(idx / ((long)N * M));
+  int r = (int)(idx - (long)g * N * M);
+  int i = r / M, j = r - i * M;
+  float v = z[idx];
+  float pr = expf(v - rmax[g * N + i]) / rsum[g * N + i];   // softmax over dim=-1
+  float out = pr;
+  if (mode != MMMOT_SM_SINGLE) {
+    float pc = expf(v - cmax[g * M + j]) / csum[g * M + j]; // softmax over dim=-2
+    if (mode == MMMOT_SM_DUAL) out = pr * pc;
+    else if (mode == MMMOT_SM_DUAL_ADD) out = (pr + pc) / 2.f;
+    else out = fmaxf(pr, pc);
+  }
+  link[idx] = out;
+}
+
+struct AfWs {
+  float *y01, *y2, *y3, *z;
+  float *sc1, *sh1, *sc0, *sh0, *sc2, *sh2, *sc3, *sh3;
+  float *v, *h1, *h2, *nsc1, *nsh1, *nsc2, *nsh2;
+  float *rmax, *rsum, *cmax, *csum;
+  double *stats, *nstats;
+  int4* tiles;
+  int* cnt;
+};
+AfWs carve(MmArena& a, int pairs, int n, int m) {
+  AfWs w;
+  size_t G = (size_t)pairs * 3, NM = (size_t)n * m, ldv = G * (n + m);
+  w.y01 = a.take<float>(G * 1024 * NM);
+  w.y2 = a.take<float>(G * 512 * NM);
+  w.y3 = a.take<float>(G * 128 * NM);
+  w.z = a.take<float>(G * NM);
+  w.sc1 = a.take<float>(G * 512); w.sh1 = a.take<float>(G * 512);
+  w.sc0 = a.take<float>(G * 512); w.sh0 = a.take<float>(G * 512);
+  w.sc2 = a.take<float>(G * 512); w.sh2 = a.take<float>(G * 512);
+  w.sc3 = a.take<float>(G * 128); w.sh3 = a.take<float>(G * 128);
+  w.v = a.take<float>(512 * ldv); w.h1 = a.take<float>(512 * ldv); w.h2 = a.take<float>(128 * ldv);
+  w.nsc1 = a.take<float>(2 * G * 512); w.nsh1 = a.take<float>(2 * G * 512);
+  w.nsc2 = a.take<float>(2 * G * 128); w.nsh2 = a.take<float>(2 * G * 128);
+  w.rmax = a.take<float>(G * n); w.rsum = a.take<float>(G * n);
+  w.cmax = a.take<float>(G * m); w.csum = a.take<float>(G * m);
+  w.stats = a.take<double>(G * 1024 * 2);
+  w.nstats = a.take<double>(2 * G * 512 * 2);
+  w.tiles = a.take<int4>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)));
+  w.cnt = a.take<int>(2 * G);
+  return w;
+}
+
+template <int MODE>
+int first_layer(GemmP& p, cudaStream_t st) { return gemm_simt_launch<MODE>(p, st); }
+
+}  // namespace
+
+extern "C" size_t mmmot_affinity_workspace(int pairs, int n, int m) {
+  MmArena a(nullptr, 0);
+  carve(a, pairs, n, m);
+  return a.off;
+}
+
+extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode, int pairs,
+                                  int n, int m, const float* feats, float* link, float* new_s,
+                                  float* end_s, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!wts || !feats || !link || !new_s || !end_s || !workspace || pairs <= 0 || n <= 0 || m <= 0)
+    return MMMOT_E_ARG;
+  if (affinity_op < 0 || affinity_op > MMMOT_AFF_MINUS || softmax_mode < 0 || softmax_mode > MMMOT_SM_DUAL_MAX)
+    return MMMOT_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  MmArena ar(workspace, workspace_bytes);
+  AfWs w = carve(ar, pairs, n, m);
+  if (!ar.ok()) return MMMOT_E_WORKSPACE;
+  const int G = pairs * 3, NM = n * m, L = n + m;
+  const int tpg = mm_cdiv(NM, 128);
+  const float* const* W = wts->w;
+
+  // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor
+  MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 1024 * 2 * sizeof(double), st));
+  {
+    GemmP p = gemm_defaults();
+    p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
+    p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
+    p.X = feats; p.n = n; p.m = m; p.Lf = L;
+    p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
+    p.stats = w.stats;
+    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? first_layer<XM_PAIR_MUL>(p, st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS ? first_layer<XM_PAIR_ABS>(p, st)
+                                                 : first_layer<XM_PAIR_SUB>(p, st);
+    if (r) return r;
+  }
+  // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),
+  // 512..1023 = conv0 -> GroupNorm(1,512) (one group over 512 x N x M; new_end.py:50)
+  MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G1W], W[MMMOT_W_AF_G1B], nullptr, NM, G, 512, 1, w.sc1, w.sh1, st, 1024, 0));
+  MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G0W], W[MMMOT_W_AF_G0B], nullptr, NM, G, 512, 512, w.sc0, w.sh0, st, 1024, 512));
+
+  // ---- new / end indicator on y0 = rows 512..1023 of y01 ----
+  const long ldv = (long)G * (n + m);
+  rowcol_mean_kernel<<<G * 512, 256, m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
+                                                             n, m, ldv, w.v);
+  MM_LAUNCH_CHECK();
+  const int tn = mm_cdiv(n, 128), tm_ = mm_cdiv(m, 128), ne_tiles = G * (tn + tm_);
+  ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G), 128), 128, 0, st>>>(G, n, m, tn, tm_, w.tiles, w.cnt);
+  MM_LAUNCH_CHECK();
+  {
+    MM_CUDA(cudaMemsetAsync(w.nstats, 0, (size_t)2 * G * 512 * 2 * sizeof(double), st));
+    GemmP p = gemm_defaults();
+    p.Wt = W[MMMOT_W_NE_W1T]; p.bias = W[MMMOT_W_NE_B1]; p.ldw = 512; p.M = 512; p.K = 512;
+    p.tile_tab = w.tiles; p.num_tiles = ne_tiles;
+    p.X = w.v; p.x_ks = ldv;
+    p.Y = w.h1; p.y_ms = ldv;
+    p.stats = w.nstats;
+    MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G1W], W[MMMOT_W_NE_G1B], w.cnt, 0, 2 * G, 512, 512, w.nsc1, w.nsh1, st));
+    MM_CUDA(cudaMemsetAsync(w.nstats, 0, (size_t)2 * G * 128 * 2 * sizeof(double), st));
+    p.Wt = W[MMMOT_W_NE_W2T]; p.bias = W[MMMOT_W_NE_B2]; p.ldw = 128; p.M = 128;
+    p.X = w.h1; p.sc = w.nsc1; p.sh = w.nsh1;
+    p.Y = w.h2;
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G2W], W[MMMOT_W_NE_G2B], w.cnt, 0, 2 * G, 128, 128, w.nsc2, w.nsh2, st));
+    ne_final_kernel<<<mm_cdiv((long)G * (n + m), 128), 128, 0, st>>>(w.h2, ldv, w.nsc2, w.nsh2, W[MMMOT_W_NE_W3],
+                                                                   W[MMMOT_W_NE_B3], G, n, m, new_s, end_s);
+    MM_LAUNCH_CHECK();
+  }
+
+  // ---- affinity MLP layers 2, 3 on y1 = rows 0..511 of y01 ----
+  {
+    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 512 * 2 * sizeof(double), st));
+    GemmP p = gemm_defaults();
+    p.Wt = W[MMMOT_W_AF_W2T]; p.bias = W[MMMOT_W_AF_B2]; p.ldw = 512; p.M = 512; p.K = 512;
+    p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
+    p.X = w.y01; p.x_gs = 1024L * NM; p.x_ks = NM; p.sc = w.sc1; p.sh = w.sh1;
+    p.Y = w.y2; p.y_gs = 512L * NM; p.y_ms = NM;
+    p.stats = w.stats;
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
+    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 128 * 2 * sizeof(double), st));
+    p.Wt = W[MMMOT_W_AF_W3T]; p.bias = W[MMMOT_W_AF_B3]; p.ldw = 128; p.M = 128;
+    p.X = w.y2; p.x_gs = 512L * NM; p.sc = w.sc2; p.sh = w.sh2;
+    p.Y = w.y3; p.y_gs = 128L * NM;
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
+  }
+  float* zdst = softmax_mode == MMMOT_SM_NONE ? link : w.z;
+  link_logit_kernel<<<mm_cdiv((long)G * NM, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
+                                                               W[MMMOT_W_AF_B4], G, NM, zdst);
+  MM_LAUNCH_CHECK();
+  if (softmax_mode != MMMOT_SM_NONE) {
+    softmax_stats_kernel<<<mm_cdiv((long)G * (n + m) * 32, 256), 256, 0, st>>>(w.z, G, n, m, w.rmax, w.rsum,
+                                                                              w.cmax, w.csum);
+    MM_LAUNCH_CHECK();
+    softmax_apply_kernel<<<mm_cdiv((long)G * NM, 256), 256, 0, st>>>(w.z, softmax_mode, G, n, m, w.rmax, w.rsum,
+                                                                    w.cmax, w.csum, link);
+    MM_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,163 @@
+// Appearance branch: VGG16-BN trunk (BN folded) + 4 SkipPool heads.
+// Replaces reference modules/appear_net.py:166-190 (vgg_forward + SkipPool.forward :27-32).
+#include "gemm_simt.cuh"
+
+namespace {
+
+// VGG16 "D" (reference modules/vgg.py:87-90): cout per conv, and whether a 2x2 max-pool follows.
+const int kVggCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+const int kVggCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
+const bool kPoolAfter[13] = {false, true, false, true, false, false, true, false, false, true, false, false, true};
+// skip map s is the output of the pool after conv 3, 6, 9, 12 (reference appear_net.py:139-152:
+// the first pool does not close a stage)
+const int kSkipAfter[13] = {-1, -1, -1, 0, -1, -1, 1, -1, -1, 2, -1, -1, 3};
+const int kSkipC[4] = {128, 256, 512, 512};
+
+// 2x2 / stride 2 max-pool, NCHW.  One thread per output pixel pair-row; float2 loads.
+__global__ void maxpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long n_out,
+                                int Ho, int Wo) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out) return;
+  int xo = (int)(idx % Wo);
+  long t = idx / Wo;
+  int yo = (int)(t % Ho);
+  long plane = t / Ho;
+  const float* src = in + (plane * (2 * Ho) + 2 * yo) * (long)(2 * Wo) + 2 * xo;
+  float2 a = *reinterpret_cast<const float2*>(src);
+  float2 b = *reinterpret_cast<const float2*>(src + 2 * Wo);
+  out[idx] = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+}
+
+// Global average pool of every (img, channel) plane: one warp per plane.
+__global__ void plane_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long planes,
+                                  int hw) {
+  long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= planes) return;
+  const float* src = in + w * hw;
+  float s = 0.f;
+  for (int i = lane; i < hw; i += 32) s += src[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[w] = s / (float)hw;
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  // 128 threads (4 warps)
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// One CTA (128 threads) per image per head: GN(1,C) -> 1x1 conv -> GN(1,mid) -> ReLU -> 1x1 conv
+// -> GN(1,128) -> ReLU.  GN(1,C) on a C x 1 x 1 input is a per-detection layer norm over channels.
+__global__ void __launch_bounds__(128) skip_head_kernel(
+    const float* __restrict__ pooled,  // [n_img][C]
+    const float* __restrict__ g0w, const float* __restrict__ g0b, const float* __restrict__ w1t,
+    const float* __restrict__ b1, const float* __restrict__ g1w, const float* __restrict__ g1b,
+    const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ g2w,
+    const float* __restrict__ g2b, int C, int mid, int L, int head, float* __restrict__ feats) {
+  __shared__ float v[512];
+  __shared__ float h[128];
+  __shared__ float red[4];
+  const int img = blockIdx.x, t = threadIdx.x;
+  const float eps = 1e-5f;
+  float s = 0.f;
+  for (int c = t; c < C; c += 128) { float x = pooled[(long)img * C + c]; v[c] = x; s += x; }
+  float mean = block_sum_128(s, red) / C;
+  s = 0.f;
+  for (int c = t; c < C; c += 128) { float d = v[c] - mean; s += d * d; }
+  float rstd = rsqrtf(block_sum_128(s, red) / C + eps);
+  for (int c = t; c < C; c += 128) v[c] = (v[c] - mean) * rstd * g0w[c] + g0b[c];
+  __syncthreads();
+  // conv C -> mid
+  float a = 0.f;
+  if (t < mid) {
+    a = b1[t];
+    for (int c = 0; c < C; c++) a = fmaf(w1t[(long)c * mid + t], v[c], a);
+  }
+  mean = block_sum_128(t < mid ? a : 0.f, red) / mid;
+  float d = t < mid ? a - mean : 0.f;
+  rstd = rsqrtf(block_sum_128(d * d, red) / mid + eps);
+  if (t < mid) h[t] = fmaxf(d * rstd * g1w[t] + g1b[t], 0.f);
+  __syncthreads();
+  // conv mid -> 128
+  a = b2[t];
+  for (int c = 0; c < mid; c++) a = fmaf(w2t[c * 128 + t], h[c], a);
+  mean = block_sum_128(a, red) / 128.f;
+  d = a - mean;
+  rstd = rsqrtf(block_sum_128(d * d, red) / 128.f + eps);
+  float o = fmaxf(d * rstd * g2w[t] + g2b[t], 0.f);
+  const int pair = img / L, l = img - pair * L;
+  feats[(((long)pair * 3 + 0) * 512 + head * 128 + t) * L + l] = o;
+}
+
+}  // namespace
+
+extern "C" size_t mmmot_appearance_workspace(int n_img, int H, int W) {
+  MmArena a(nullptr, 0);
+  size_t act = (size_t)n_img * 64 * H * W;
+  a.take<float>(act);
+  a.take<float>(act);
+  for (int s = 0; s < 4; s++) a.take<float>((size_t)n_img * kSkipC[s]);
+  return a.off;
+}
+
+extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops, int n_img, int H,
+                                    int W, int L, float* feats, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!wts || !crops || !feats || !workspace || n_img <= 0 || L <= 0) return MMMOT_E_ARG;
+  if (H % 32 || W % 32 || H <= 0 || W <= 0 || n_img % L) return MMMOT_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  MmArena ar(workspace, workspace_bytes);
+  size_t act = (size_t)n_img * 64 * H * W;
+  float* buf[2] = {ar.take<float>(act), ar.take<float>(act)};
+  float* pooled[4];
+  for (int s = 0; s < 4; s++) pooled[s] = ar.take<float>((size_t)n_img * kSkipC[s]);
+  if (!ar.ok()) return MMMOT_E_WORKSPACE;
+
+  const float* cur = crops;
+  int which = 0, h = H, w = W;
+  for (int i = 0; i < 13; i++) {
+    GemmP p = gemm_defaults();
+    p.Wt = wts->w[MMMOT_W_VGG_WT0 + i];
+    p.bias = wts->w[MMMOT_W_VGG_B0 + i];
+    p.ldw = kVggCout[i];
+    p.M = kVggCout[i];
+    p.K = 9 * kVggCin[i];
+    p.Cin = kVggCin[i];
+    p.H = h; p.W = w;
+    p.S = n_img * h * w;
+    p.tiles_per_group = mm_cdiv(p.S, 128);
+    p.num_tiles = p.tiles_per_group;
+    p.X = cur;
+    p.Y = buf[which];
+    p.relu = 1;
+    MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
+    cur = buf[which]; which ^= 1;
+    if (kPoolAfter[i]) {
+      h /= 2; w /= 2;
+      long n_out = (long)n_img * kVggCout[i] * h * w;
+      maxpool2_kernel<<<mm_cdiv(n_out, 256), 256, 0, st>>>(cur, buf[which], n_out, h, w);
+      MM_LAUNCH_CHECK();
+      cur = buf[which]; which ^= 1;
+      int s = kSkipAfter[i];
+      if (s >= 0) {
+        long planes = (long)n_img * kSkipC[s];
+        plane_mean_kernel<<<mm_cdiv(planes * 32, 256), 256, 0, st>>>(cur, pooled[s], planes, h * w);
+        MM_LAUNCH_CHECK();
+      }
+    }
+  }
+  for (int s = 0; s < 4; s++) {
+    const float* const* q = &wts->w[MMMOT_W_SKIP0 + 10 * s];
+    int C = kSkipC[s], mid = C / 4 > 64 ? C / 4 : 64;
+    skip_head_kernel<<<n_img, 128, 0, st>>>(pooled[s], q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7],
+                                            q[8], q[9], C, mid, L, s, feats);
+    MM_LAUNCH_CHECK();
+  }
+  return 0;
+}

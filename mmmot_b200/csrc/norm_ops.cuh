@@ -1,0 +1,42 @@
+// GroupNorm statistics -> per-(group, channel) affine, and a few small shared kernels.
+#pragma once
+#include "common.cuh"
+
+// stats[G][C][2] (sum, sumsq over the group's columns, fp64) -> sc/sh[G][C] so that
+//   GroupNorm(x)[c] = x*sc + sh,   sc = gamma[c]*rstd,  sh = beta[c] - mean*sc.
+// The statistics row of group g is stats[g*stats_ld + c_off + c] (lets two GroupNorms share one
+// stacked contraction).
+// cpg = channels per normalisation group (1: GroupNorm(C,C); C: GroupNorm(1,C); 32: GroupNorm(16,512)).
+// count = columns per group: cnt[g] if cnt != null else `uniform`.  Biased variance, eps 1e-5
+// (torch.nn.GroupNorm semantics; a 1-element group yields exactly beta).
+static __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const int* __restrict__ cnt,
+                                   int uniform, int G, int C, int cpg, int stats_ld, int c_off,
+                                   float* __restrict__ sc, float* __restrict__ sh) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * C) return;
+  int g = idx / C, c = idx - g * C;
+  int c0 = c / cpg * cpg;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < cpg; k++) {
+    s1 += stats[((long)g * stats_ld + c_off + c0 + k) * 2];
+    s2 += stats[((long)g * stats_ld + c_off + c0 + k) * 2 + 1];
+  }
+  double n = (double)(cnt ? cnt[g] : uniform) * cpg;
+  double mean = s1 / n;
+  double var = s2 / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double rstd = 1.0 / sqrt(var + 1e-5);
+  double a = (double)gamma[c] * rstd;
+  sc[idx] = (float)a;
+  sh[idx] = (float)((double)beta[c] - mean * a);
+}
+
+static inline int gn_finalize(const double* stats, const float* gamma, const float* beta, const int* cnt,
+                              int uniform, int G, int C, int cpg, float* sc, float* sh,
+                              cudaStream_t st, int stats_ld = 0, int c_off = 0) {
+  gn_finalize_kernel<<<mm_cdiv((long)G * C, 256), 256, 0, st>>>(
+      stats, gamma, beta, cnt, uniform, G, C, cpg, stats_ld ? stats_ld : C, c_off, sc, sh);
+  MM_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,208 @@
+// PointNet encoder over ragged per-detection LiDAR point sets.
+// Replaces reference modules/point_net.py:25-44 (PointNet_v1.forward) and :115-153
+// (PointNetfeatGN.forward).  Uses two identities proven in SURVEY F4 / B-9:
+//   * both STN transforms are input-independent constants -> folded into conv1 / conv2 / head
+//     weights by the host weight packer (the STN convs are never executed);
+//   * the 1088-wide head conv splits into a 64-wide per-point part plus a per-detection
+//     addend  Wh[:,64:] * mean_det(x5)  (1088 -> 64 MACs per point per output channel).
+// Per-detection pooling is a MEAN.  One frame-pair = one GroupNorm domain.
+#include <vector>
+
+#include "gemm_simt.cuh"
+#include "norm_ops.cuh"
+
+namespace {
+
+__global__ void transpose_points_kernel(const float* __restrict__ pts, float* __restrict__ xt, long P) {
+  long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  xt[p] = pts[p * 3];
+  xt[P + p] = pts[p * 3 + 1];
+  xt[2 * P + p] = pts[p * 3 + 2];
+}
+
+// seg[p] = detection owning point p (binary search in the CSR offsets)
+__global__ void point_segment_kernel(const int* __restrict__ split, int ndet, long P, int* __restrict__ seg) {
+  long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int lo = 0, hi = ndet;  // split[lo] <= p < split[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (split[mid] <= p) lo = mid; else hi = mid;
+  }
+  seg[p] = lo;
+}
+
+// out[c][d] = mean over the detection's points of relu(Y[c][p]*sc[pair][c] + sh[pair][c]).
+// One warp per (c, d); lanes stride the segment (coalesced).
+__global__ void segment_mean_kernel(const float* __restrict__ Y, long P, const int* __restrict__ split,
+                                    const float* __restrict__ sc, const float* __restrict__ sh, int C,
+                                    int ndet, int L, float* __restrict__ out) {
+  long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= (long)C * ndet) return;
+  int d = (int)(w % ndet), c = (int)(w / ndet);
+  int pair = d / L;
+  float a = sc[(long)pair * C + c], b = sh[(long)pair * C + c];
+  int s = split[d], e = split[d + 1];
+  const float* row = Y + (long)c * P;
+  float acc = 0.f;
+  for (int p = s + lane; p < e; p += 32) acc += fmaxf(fmaf(row[p], a, b), 0.f);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[(long)c * ndet + d] = e > s ? acc / (float)(e - s) : 0.f;
+}
+
+// feats[pair][1][c][l] = relu(O[c][d]*sc[pair][c] + sh[pair][c])
+__global__ void pointnet_out_kernel(const float* __restrict__ O, const float* __restrict__ sc,
+                                    const float* __restrict__ sh, int ndet, int L,
+                                    float* __restrict__ feats) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 512L * ndet) return;
+  int d = (int)(idx % ndet), c = (int)(idx / ndet);
+  int pair = d / L, l = d - pair * L;
+  float v = fmaxf(fmaf(O[idx], sc[pair * 512 + c], sh[pair * 512 + c]), 0.f);
+  feats[(((long)pair * 3 + 1) * 512 + c) * L + l] = v;
+}
+
+struct PnWs {
+  float *xt, *y1, *t0, *t1, *big, *gmean, *u, *hmean, *o;
+  float *sc1, *sh1, *sc, *sh;
+  double* stats;
+  int *seg, *cnt;
+  int4* tiles;
+};
+
+PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
+  PnWs w;
+  long nd = (long)pairs * L;
+  w.xt = a.take<float>(3 * P);
+  w.y1 = a.take<float>(64 * P);
+  w.t0 = a.take<float>(128 * P);
+  w.t1 = a.take<float>(64 * P);
+  w.big = a.take<float>(1024 * P);
+  w.gmean = a.take<float>(1024 * nd);
+  w.u = a.take<float>(512 * nd);
+  w.hmean = a.take<float>(512 * nd);
+  w.o = a.take<float>(512 * nd);
+  w.sc1 = a.take<float>((size_t)pairs * 64);
+  w.sh1 = a.take<float>((size_t)pairs * 64);
+  w.sc = a.take<float>((size_t)pairs * 1024);
+  w.sh = a.take<float>((size_t)pairs * 1024);
+  w.stats = a.take<double>((size_t)pairs * 1024 * 2);
+  w.seg = a.take<int>(P);
+  w.cnt = a.take<int>(pairs);
+  w.tiles = a.take<int4>(max_tiles);
+  return w;
+}
+
+}  // namespace
+
+extern "C" size_t mmmot_pointnet_workspace(int pairs, int L, long p_total) {
+  MmArena a(nullptr, 0);
+  carve(a, pairs, L, p_total, p_total / 128 + pairs + 1);
+  return a.off;
+}
+
+extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points, const int* det_split,
+                                  const int* h_det_split, int pairs, int L, float* feats,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (!wts || !points || !det_split || !h_det_split || !feats || !workspace || pairs <= 0 || L <= 0)
+    return MMMOT_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ndet = pairs * L;
+  const long P = h_det_split[ndet];
+  if (h_det_split[0] != 0 || P <= 0) return MMMOT_E_SHAPE;
+  for (int d = 0; d < ndet; d++)
+    if (h_det_split[d + 1] <= h_det_split[d]) return MMMOT_E_SHAPE;  // every detection owns >= 1 point
+
+  // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
+  std::vector<int4> tiles;
+  std::vector<int> cnt(pairs);
+  for (int p = 0; p < pairs; p++) {
+    int s = h_det_split[p * L], e = h_det_split[(p + 1) * L];
+    cnt[p] = e - s;
+    for (int c = s; c < e; c += 128) tiles.push_back(make_int4(p, c, min(128, e - c), 0));
+  }
+  const long max_tiles = P / 128 + pairs + 1;
+  MmArena ar(workspace, workspace_bytes);
+  PnWs w = carve(ar, pairs, L, P, max_tiles);
+  if (!ar.ok() || (long)tiles.size() > max_tiles) return MMMOT_E_WORKSPACE;
+  MM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(w.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  transpose_points_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(points, w.xt, P);
+  MM_LAUNCH_CHECK();
+  point_segment_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(det_split, ndet, P, w.seg);
+  MM_LAUNCH_CHECK();
+
+  // trunk: 3 -> 64 -> 64 -> 64 -> 128 -> 1024, each conv + GroupNorm(C,C) over the pair's points + ReLU
+  const int cin[5] = {3, 64, 64, 64, 128}, cout[5] = {64, 64, 64, 128, 1024};
+  const float* src[5] = {w.xt, w.y1, w.t0, w.t1, w.t0};
+  float* dst[5] = {w.y1, w.t0, w.t1, w.t0, w.big};
+  for (int i = 0; i < 5; i++) {
+    const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
+    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * cout[i] * 2 * sizeof(double), st));
+    GemmP p = gemm_defaults();
+    p.Wt = q[0]; p.bias = q[1]; p.ldw = cout[i]; p.M = cout[i]; p.K = cin[i];
+    p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+    p.X = src[i]; p.x_ks = P;
+    p.Y = dst[i]; p.y_ms = P;
+    p.stats = w.stats;
+    if (i == 0) {
+      MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    } else {
+      p.sc = (i == 1) ? w.sc1 : w.sc;
+      p.sh = (i == 1) ? w.sh1 : w.sh;
+      MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    }
+    MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, i == 0 ? w.sc1 : w.sc,
+                       i == 0 ? w.sh1 : w.sh, st));
+  }
+  // per-detection mean of the 1024-d feature (reference point_net.py:140-146)
+  segment_mean_kernel<<<mm_cdiv(1024L * ndet * 32, 256), 256, 0, st>>>(w.big, P, det_split, w.sc, w.sh,
+                                                                       1024, ndet, L, w.gmean);
+  MM_LAUNCH_CHECK();
+  // U = Wh[:,64:] * gmean  (the per-detection part of point_net.py:27-28's conv1)
+  {
+    GemmP p = gemm_defaults();
+    p.Wt = wts->w[MMMOT_W_PN_WHGT]; p.ldw = 512; p.M = 512; p.K = 1024;
+    p.S = ndet; p.tiles_per_group = mm_cdiv(ndet, 128); p.num_tiles = p.tiles_per_group;
+    p.X = w.gmean; p.x_ks = ndet;
+    p.Y = w.u; p.y_ms = ndet;
+    MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+  }
+  // head: Wh[:, :64] * x_local + U[:, det(p)] + b -> GroupNorm(512,512) -> ReLU -> per-detection mean
+  {
+    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * 512 * 2 * sizeof(double), st));
+    GemmP p = gemm_defaults();
+    p.Wt = wts->w[MMMOT_W_PN_WHAT]; p.bias = wts->w[MMMOT_W_PN_BH]; p.ldw = 512; p.M = 512; p.K = 64;
+    p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+    p.X = w.y1; p.x_ks = P; p.sc = w.sc1; p.sh = w.sh1;
+    p.Y = w.big; p.y_ms = P;
+    p.stats = w.stats;
+    p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,
+                       w.sc, w.sh, st));
+    segment_mean_kernel<<<mm_cdiv(512L * ndet * 32, 256), 256, 0, st>>>(w.big, P, det_split, w.sc, w.sh,
+                                                                        512, ndet, L, w.hmean);
+    MM_LAUNCH_CHECK();
+  }
+  // conv2 512 -> 512 over the pair's L detections, GroupNorm(16,512), ReLU (point_net.py:40-41)
+  {
+    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * 512 * 2 * sizeof(double), st));
+    GemmP p = gemm_defaults();
+    p.Wt = wts->w[MMMOT_W_PN_WOT]; p.bias = wts->w[MMMOT_W_PN_BO]; p.ldw = 512; p.M = 512; p.K = 512;
+    p.S = L; p.tiles_per_group = mm_cdiv(L, 128); p.num_tiles = p.tiles_per_group * pairs;
+    p.X = w.hmean; p.x_gs = L; p.x_ks = ndet;
+    p.Y = w.o; p.y_gs = L; p.y_ms = ndet;
+    p.stats = w.stats;
+    MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GOW], wts->w[MMMOT_W_PN_GOB], nullptr, L, pairs, 512, 32,
+                       w.sc, w.sh, st));
+    pointnet_out_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.o, w.sc, w.sh, ndet, L, feats);
+    MM_LAUNCH_CHECK();
+  }
+  return 0;
+}
