@@ -161,6 +161,13 @@ int mmmot_lp_assign(const float* det, long det_stride, const float* link, long l
                     float* a_det, float* a_link, float* a_new, float* a_end, int* match,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
+ * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed
+ * duration (ms), the summed algorithmic FLOPs (2*Cout*9Cin*pixels) and the launch count of every
+ * timed launch since the last collect(). */
+int mmmot_timing_enable(int on);
+int mmmot_timing_collect(double* total_ms, double* total_flop, long* launches);
+
 /* counts kernel launches made through this library since process start (bench.py gpu_launches) */
 unsigned long long mmmot_launch_count(void);
 

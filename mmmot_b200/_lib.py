@@ -46,6 +46,8 @@ SIGNATURES = {
     "mmmot_abi_version": (_i, []),
     "mmmot_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "mmmot_launch_count": (ctypes.c_ulonglong, []),
+    "mmmot_timing_enable": (_i, [_i]),
+    "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),
     "mmmot_appearance_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmmot_pointnet_workspace": (_sz, [_i, _i, _l]),

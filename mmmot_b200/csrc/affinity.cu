@@ -18,14 +18,12 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
                                                           const float* __restrict__ sc,
                                                           const float* __restrict__ sh, int N, int M,
                                                           long ldv, float* __restrict__ V) {
-  extern __shared__ float colacc[];  // [M]
+  extern __shared__ float colacc[];  // [warps][M]: per-warp partial column sums, combined in fixed order
   const int g = blockIdx.x / 512, c = blockIdx.x % 512;
   const float a = sc[g * 512 + c], b = sh[g * 512 + c];
   const float* src = y0 + (long)g * y_gs + (long)c * N * M;
   float* vout = V + (long)c * ldv + (long)g * (M + N);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = threadIdx.x; j < M; j += blockDim.x) colacc[j] = 0.f;
-  __syncthreads();
   // each warp owns rows i = warp, warp+nw, ...; lanes stride the columns
   for (int j0 = 0; j0 < M; j0 += 32) {
     const int j = j0 + lane;
@@ -33,7 +31,7 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
     for (int i = warp; i < N; i += nw) {
       if (j < M) cs += fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f);
     }
-    if (j < M) atomicAdd(&colacc[j], cs);
+    if (j < M) colacc[warp * M + j] = cs;
   }
   for (int i = warp; i < N; i += nw) {
     float rs = 0.f;
@@ -43,15 +41,20 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
     if (lane == 0) vout[M + i] = rs / (float)M;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < M; j += blockDim.x) vout[j] = colacc[j] / (float)N;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < nw; w2++) t += colacc[w2 * M + j];
+    vout[j] = t / (float)N;
+  }
 }
 
 // Tile table for the new/end MLP: group 2g = new columns (len M), 2g+1 = end columns (len N).
 __global__ void ne_tiles_kernel(int G, int N, int M, int tn, int tm_, int4* __restrict__ tiles,
-                                int* __restrict__ cnt) {
+                                int* __restrict__ cnt, int* __restrict__ gstart) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int per = tm_ + tn;  // tiles per g: tm_ for the M new columns, tn for the N end columns
-  if (idx < G * 2) cnt[idx] = (idx & 1) ? N : M;
+  if (idx < G * 2) { cnt[idx] = (idx & 1) ? N : M; gstart[idx] = (idx >> 1) * per + ((idx & 1) ? tm_ : 0); }
+  if (idx == G * 2) gstart[idx] = G * per;
   if (idx >= G * per) return;
   int g = idx / per, t = idx - g * per;
   if (t < tm_) tiles[idx] = make_int4(2 * g, g * (M + N) + t * 128, min(128, M - t * 128), 0);
@@ -145,7 +148,8 @@ struct AfWs {
   float *rmax, *rsum, *cmax, *csum;
   double *stats, *nstats;
   int4* tiles;
-  int* cnt;
+  int *cnt, *gstart;
+  double2 *part, *npart;
 };
 AfWs carve(MmArena& a, int pairs, int n, int m) {
   AfWs w;
@@ -167,6 +171,9 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.nstats = a.take<double>(2 * G * 512 * 2);
   w.tiles = a.take<int4>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)));
   w.cnt = a.take<int>(2 * G);
+  w.gstart = a.take<int>(2 * G + 1);
+  w.part = a.take<double2>(G * mm_cdiv(NM, 128) * 1024);
+  w.npart = a.take<double2>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);
   return w;
 }
 
@@ -197,14 +204,13 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   const float* const* W = wts->w;
 
   // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor
-  MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 1024 * 2 * sizeof(double), st));
   {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.X = feats; p.n = n; p.m = m; p.Lf = L;
     p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
-    p.stats = w.stats;
+    p.part = w.part;
     int r = affinity_op == MMMOT_AFF_MULTIPLY    ? first_layer<XM_PAIR_MUL>(p, st)
             : affinity_op == MMMOT_AFF_MINUS_ABS ? first_layer<XM_PAIR_ABS>(p, st)
                                                  : first_layer<XM_PAIR_SUB>(p, st);
@@ -212,32 +218,33 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   }
   // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),
   // 512..1023 = conv0 -> GroupNorm(1,512) (one group over 512 x N x M; new_end.py:50)
+  MM_TRY(stats_reduce(w.part, 1024, G, tpg, nullptr, w.stats, st));
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G1W], W[MMMOT_W_AF_G1B], nullptr, NM, G, 512, 1, w.sc1, w.sh1, st, 1024, 0));
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G0W], W[MMMOT_W_AF_G0B], nullptr, NM, G, 512, 512, w.sc0, w.sh0, st, 1024, 512));
 
   // ---- new / end indicator on y0 = rows 512..1023 of y01 ----
   const long ldv = (long)G * (n + m);
-  rowcol_mean_kernel<<<G * 512, 256, m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
+  rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
                                                              n, m, ldv, w.v);
   MM_LAUNCH_CHECK();
   const int tn = mm_cdiv(n, 128), tm_ = mm_cdiv(m, 128), ne_tiles = G * (tn + tm_);
-  ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G), 128), 128, 0, st>>>(G, n, m, tn, tm_, w.tiles, w.cnt);
+  ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G + 1), 128), 128, 0, st>>>(G, n, m, tn, tm_, w.tiles, w.cnt, w.gstart);
   MM_LAUNCH_CHECK();
   {
-    MM_CUDA(cudaMemsetAsync(w.nstats, 0, (size_t)2 * G * 512 * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_NE_W1T]; p.bias = W[MMMOT_W_NE_B1]; p.ldw = 512; p.M = 512; p.K = 512;
     p.tile_tab = w.tiles; p.num_tiles = ne_tiles;
     p.X = w.v; p.x_ks = ldv;
     p.Y = w.h1; p.y_ms = ldv;
-    p.stats = w.nstats;
+    p.part = w.npart;
     MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    MM_TRY(stats_reduce(w.npart, 512, 2 * G, 0, w.gstart, w.nstats, st));
     MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G1W], W[MMMOT_W_NE_G1B], w.cnt, 0, 2 * G, 512, 512, w.nsc1, w.nsh1, st));
-    MM_CUDA(cudaMemsetAsync(w.nstats, 0, (size_t)2 * G * 128 * 2 * sizeof(double), st));
     p.Wt = W[MMMOT_W_NE_W2T]; p.bias = W[MMMOT_W_NE_B2]; p.ldw = 128; p.M = 128;
     p.X = w.h1; p.sc = w.nsc1; p.sh = w.nsh1;
     p.Y = w.h2;
     MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(stats_reduce(w.npart, 128, 2 * G, 0, w.gstart, w.nstats, st));
     MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G2W], W[MMMOT_W_NE_G2B], w.cnt, 0, 2 * G, 128, 128, w.nsc2, w.nsh2, st));
     ne_final_kernel<<<mm_cdiv((long)G * (n + m), 128), 128, 0, st>>>(w.h2, ldv, w.nsc2, w.nsh2, W[MMMOT_W_NE_W3],
                                                                    W[MMMOT_W_NE_B3], G, n, m, new_s, end_s);
@@ -246,20 +253,20 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
 
   // ---- affinity MLP layers 2, 3 on y1 = rows 0..511 of y01 ----
   {
-    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 512 * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W2T]; p.bias = W[MMMOT_W_AF_B2]; p.ldw = 512; p.M = 512; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.X = w.y01; p.x_gs = 1024L * NM; p.x_ks = NM; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.y2; p.y_gs = 512L * NM; p.y_ms = NM;
-    p.stats = w.stats;
+    p.part = w.part;
     MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
-    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)G * 128 * 2 * sizeof(double), st));
     p.Wt = W[MMMOT_W_AF_W3T]; p.bias = W[MMMOT_W_AF_B3]; p.ldw = 128; p.M = 128;
     p.X = w.y2; p.x_gs = 512L * NM; p.sc = w.sc2; p.sh = w.sh2;
     p.Y = w.y3; p.y_gs = 128L * NM;
     MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   }
   float* zdst = softmax_mode == MMMOT_SM_NONE ? link : w.z;

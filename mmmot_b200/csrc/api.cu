@@ -21,3 +21,60 @@ extern "C" int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) *cc_minor = prop.minor;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-launch timing of the dominant kernel (the 3x3-conv contraction), used by bench.py
+// for the roofline figure: CUDA events recorded on the launching stream around every launch
+// while enabled; mmmot_timing_collect() synchronises on the events and returns the totals.
+#include <mutex>
+#include <vector>
+
+namespace {
+std::mutex g_tmu;
+bool g_timing = false;
+struct Span { cudaEvent_t a, b; double flop; };
+std::vector<Span> g_spans;
+}  // namespace
+
+bool mm_timing_on() { return g_timing; }
+
+void mm_timing_begin(cudaStream_t st, double flop) {
+  std::lock_guard<std::mutex> l(g_tmu);
+  Span s;
+  cudaEventCreate(&s.a);
+  cudaEventCreate(&s.b);
+  s.flop = flop;
+  cudaEventRecord(s.a, st);
+  g_spans.push_back(s);
+}
+
+void mm_timing_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> l(g_tmu);
+  if (!g_spans.empty()) cudaEventRecord(g_spans.back().b, st);
+}
+
+extern "C" int mmmot_timing_enable(int on) {
+  std::lock_guard<std::mutex> l(g_tmu);
+  g_timing = on != 0;
+  return 0;
+}
+
+extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* launches) {
+  std::lock_guard<std::mutex> l(g_tmu);
+  double ms = 0.0, fl = 0.0;
+  long n = 0;
+  for (auto& s : g_spans) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(s.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.a, s.b);
+    if (e != cudaSuccess) return (int)e;
+    ms += t; fl += s.flop; n++;
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  g_spans.clear();
+  if (total_ms) *total_ms = ms;
+  if (total_flop) *total_flop = fl;
+  if (launches) *launches = n;
+  return 0;
+}

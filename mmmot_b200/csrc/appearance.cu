@@ -136,7 +136,10 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     p.X = cur;
     p.Y = buf[which];
     p.relu = 1;
+    const bool timed = mm_timing_on();
+    if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
     MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
+    if (timed) mm_timing_end(st);
     cur = buf[which]; which ^= 1;
     if (kPoolAfter[i]) {
       h /= 2; w /= 2;

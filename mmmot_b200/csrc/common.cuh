@@ -26,6 +26,9 @@
   } while (0)
 
 void mm_count_launch();
+bool mm_timing_on();
+void mm_timing_begin(cudaStream_t st, double flop);
+void mm_timing_end(cudaStream_t st);
 
 static inline size_t mm_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline int mm_cdiv(long a, long b) { return (int)((a + b - 1) / b); }

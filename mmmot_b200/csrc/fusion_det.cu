@@ -51,6 +51,7 @@ __global__ void det_score_kernel(const float* __restrict__ h2, const float* __re
 struct FdWs {
   float *yp, *yi, *gp, *gi, *scp, *shp, *sci, *shi, *h1, *h2;
   double* stats;
+  double2* part;
 };
 FdWs carve(MmArena& a, int pairs, int L) {
   FdWs w;
@@ -61,6 +62,7 @@ FdWs carve(MmArena& a, int pairs, int L) {
   w.h1 = a.take<float>(3 * n);
   w.h2 = a.take<float>(3 * n / 2);
   w.stats = a.take<double>((size_t)pairs * 512 * 2);
+  w.part = a.take<double2>((size_t)pairs * mm_cdiv(L, 128) * 512);
   return w;
 }
 
@@ -87,14 +89,14 @@ extern "C" int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, f
   // linear (+ optional GroupNorm statistics) on one modality: X = feats[pair][stack]
   auto linear = [&](int wt, int wb, int K, int stack, float* Y, bool stats, int gw, int gb, float* sc,
                     float* sh) -> int {
-    if (stats) MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * 512 * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = wts->w[wt]; p.bias = wts->w[wb]; p.ldw = 512; p.M = 512; p.K = K;
     p.S = L; p.tiles_per_group = tpg; p.num_tiles = tpg * pairs;
     p.X = feats + (long)stack * 512 * L; p.x_gs = fs; p.x_ks = L;
     p.Y = Y; p.y_gs = 512L * L; p.y_ms = L;
-    p.stats = stats ? w.stats : nullptr;
+    p.part = stats ? w.part : nullptr;
     MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    if (stats) MM_TRY(stats_reduce(w.part, 512, pairs, tpg, nullptr, w.stats, st));
     if (stats) MM_TRY(gn_finalize(w.stats, wts->w[gw], wts->w[gb], nullptr, L, pairs, 512, 1, sc, sh, st));
     return 0;
   };

@@ -8,7 +8,8 @@
 //                                                                the 3xDxNxM tensor is never stored)
 //   XM_CONV3      Xin = im2col of a 3x3 / pad 1 convolution, k = (ky*3+kx)*Cin + ci, s = (img,y,x)
 // and a fused epilogue: bias, optional per-(detection) addend, optional ReLU, optional
-// per-(group, channel) sum / sum-of-squares for the following GroupNorm (fp64 atomics).
+// per-(tile, channel) sum / sum-of-squares partials for the following GroupNorm (fp64, reduced in a
+// fixed order afterwards, so results are bit-reproducible).
 //
 // This is the accuracy-first engine (plain FP32 FFMA, 128x128x16 tiles, 8x8 register blocking).
 // fp32-exact operand arithmetic is what the 1e-4 parity bound needs.
@@ -42,7 +43,8 @@ struct GemmP {
   // output: Y + g*y_gs + co*y_ms + col ; null = statistics only
   float* Y;
   long y_gs, y_ms;
-  double* stats;        // [G][M][2] (sum, sumsq) or null
+  double2* part;        // [num_tiles][M] per-tile (sum, sumsq) partials or null; reduced in fixed
+                        // order by stats_reduce (no atomics: results are run-to-run bit-identical)
   const float* addend;  // Y += addend[co*ld_add + seg[col]] or null
   const int* seg;
   int ld_add;
@@ -269,18 +271,14 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(const GemmP p) {
         }
       }
     }
-    if (p.stats) {
+    if (p.part) {
       double d1 = s1, d2 = s2;
 #pragma unroll
       for (int o = 8; o >= 1; o >>= 1) {
         d1 += __shfl_xor_sync(0xffffffffu, d1, o);
         d2 += __shfl_xor_sync(0xffffffffu, d2, o);
       }
-      if (tx == 0) {
-        double* st = p.stats + ((long)g * p.M + co) * 2;
-        atomicAdd(st, d1);
-        atomicAdd(st + 1, d2);
-      }
+      if (tx == 0) p.part[(long)nt * p.M + co] = make_double2(d1, d2);
     }
   }
 }

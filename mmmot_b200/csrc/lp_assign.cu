@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lp_assign_kernel(
     for (int j = lane; j <= nc; j += 32) { minv[j] = INF; used[j] = 0; }
     __syncwarp();
     int j0 = 0;
-    while (true) {
+    // every pass marks one more column used, so nc + 1 passes bound the search (guard against hangs)
+    for (int pass = 0; pass <= nc; pass++) {
       if (lane == 0) used[j0] = 1;
       __syncwarp();
       const int i0 = p[j0];

@@ -9,6 +9,32 @@
 // cpg = channels per normalisation group (1: GroupNorm(C,C); C: GroupNorm(1,C); 32: GroupNorm(16,512)).
 // count = columns per group: cnt[g] if cnt != null else `uniform`.  Biased variance, eps 1e-5
 // (torch.nn.GroupNorm semantics; a 1-element group yields exactly beta).
+// Fixed-order reduction of the contraction engine's per-tile partials: stats[g][c] = sum over the
+// group's tiles (ascending) of part[tile][c].  Group g owns tiles [g*tpg, (g+1)*tpg) (uniform) or
+// [gstart[g], gstart[g+1]) (table tiling).
+static __global__ void stats_reduce_kernel(const double2* __restrict__ part, int M, int G, int tpg,
+                                           const int* __restrict__ gstart, double* __restrict__ stats) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= G * M) return;
+  int g = idx / M, c = idx - g * M;
+  int t0 = gstart ? gstart[g] : g * tpg, t1 = gstart ? gstart[g + 1] : (g + 1) * tpg;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = t0; t < t1; t++) {
+    double2 v = part[(long)t * M + c];
+    s1 += v.x;
+    s2 += v.y;
+  }
+  stats[(long)idx * 2] = s1;
+  stats[(long)idx * 2 + 1] = s2;
+}
+
+static inline int stats_reduce(const double2* part, int M, int G, int tpg, const int* gstart, double* stats,
+                               cudaStream_t st) {
+  stats_reduce_kernel<<<mm_cdiv((long)G * M, 128), 128, 0, st>>>(part, M, G, tpg, gstart, stats);
+  MM_LAUNCH_CHECK();
+  return 0;
+}
+
 static __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const int* __restrict__ cnt,
                                    int uniform, int G, int C, int cpg, int stats_ld, int c_off,

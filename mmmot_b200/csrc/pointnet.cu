@@ -69,7 +69,8 @@ struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *hmean, *o;
   float *sc1, *sh1, *sc, *sh;
   double* stats;
-  int *seg, *cnt;
+  double2* part;
+  int *seg, *cnt, *gstart;
   int4* tiles;
 };
 
@@ -90,6 +91,8 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
   w.sc = a.take<float>((size_t)pairs * 1024);
   w.sh = a.take<float>((size_t)pairs * 1024);
   w.stats = a.take<double>((size_t)pairs * 1024 * 2);
+  w.part = a.take<double2>((size_t)max_tiles * 1024);
+  w.gstart = a.take<int>(pairs + 1);
   w.seg = a.take<int>(P);
   w.cnt = a.take<int>(pairs);
   w.tiles = a.take<int4>(max_tiles);
@@ -118,18 +121,21 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
 
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
   std::vector<int4> tiles;
-  std::vector<int> cnt(pairs);
+  std::vector<int> cnt(pairs), gstart(pairs + 1);
   for (int p = 0; p < pairs; p++) {
     int s = h_det_split[p * L], e = h_det_split[(p + 1) * L];
     cnt[p] = e - s;
+    gstart[p] = (int)tiles.size();
     for (int c = s; c < e; c += 128) tiles.push_back(make_int4(p, c, min(128, e - c), 0));
   }
+  gstart[pairs] = (int)tiles.size();
   const long max_tiles = P / 128 + pairs + 1;
   MmArena ar(workspace, workspace_bytes);
   PnWs w = carve(ar, pairs, L, P, max_tiles);
   if (!ar.ok() || (long)tiles.size() > max_tiles) return MMMOT_E_WORKSPACE;
   MM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(w.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(w.gstart, gstart.data(), gstart.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 
   transpose_points_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(points, w.xt, P);
   MM_LAUNCH_CHECK();
@@ -142,13 +148,12 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   float* dst[5] = {w.y1, w.t0, w.t1, w.t0, w.big};
   for (int i = 0; i < 5; i++) {
     const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
-    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * cout[i] * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = q[0]; p.bias = q[1]; p.ldw = cout[i]; p.M = cout[i]; p.K = cin[i];
     p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
     p.X = src[i]; p.x_ks = P;
     p.Y = dst[i]; p.y_ms = P;
-    p.stats = w.stats;
+    p.part = w.part;
     if (i == 0) {
       MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
     } else {
@@ -156,6 +161,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       p.sh = (i == 1) ? w.sh1 : w.sh;
       MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     }
+    MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, i == 0 ? w.sc1 : w.sc,
                        i == 0 ? w.sh1 : w.sh, st));
   }
@@ -174,15 +180,15 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   }
   // head: Wh[:, :64] * x_local + U[:, det(p)] + b -> GroupNorm(512,512) -> ReLU -> per-detection mean
   {
-    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * 512 * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = wts->w[MMMOT_W_PN_WHAT]; p.bias = wts->w[MMMOT_W_PN_BH]; p.ldw = 512; p.M = 512; p.K = 64;
     p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
     p.X = w.y1; p.x_ks = P; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.big; p.y_ms = P;
-    p.stats = w.stats;
+    p.part = w.part;
     p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
     MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,
                        w.sc, w.sh, st));
     segment_mean_kernel<<<mm_cdiv(512L * ndet * 32, 256), 256, 0, st>>>(w.big, P, det_split, w.sc, w.sh,
@@ -191,14 +197,14 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   }
   // conv2 512 -> 512 over the pair's L detections, GroupNorm(16,512), ReLU (point_net.py:40-41)
   {
-    MM_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)pairs * 512 * 2 * sizeof(double), st));
     GemmP p = gemm_defaults();
     p.Wt = wts->w[MMMOT_W_PN_WOT]; p.bias = wts->w[MMMOT_W_PN_BO]; p.ldw = 512; p.M = 512; p.K = 512;
     p.S = L; p.tiles_per_group = mm_cdiv(L, 128); p.num_tiles = p.tiles_per_group * pairs;
     p.X = w.hmean; p.x_gs = L; p.x_ks = ndet;
     p.Y = w.o; p.y_gs = L; p.y_ms = ndet;
-    p.stats = w.stats;
+    p.part = w.part;
     MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    MM_TRY(stats_reduce(w.part, 512, pairs, p.tiles_per_group, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GOW], wts->w[MMMOT_W_PN_GOB], nullptr, L, pairs, 512, 32,
                        w.sc, w.sh, st));
     pointnet_out_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.o, w.sc, w.sh, ndet, L, feats);

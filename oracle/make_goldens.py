@@ -23,7 +23,7 @@ CASES = [
     ("subabs_dualadd_C_n8", "C", "minus_abs", "dual_add", 0.2, 8, 8, 32, 32, True, 4),
     ("rrc_subabs_dualadd_C_n5x3", "C", "minus_abs", "dual_add", 0.0, 5, 3, 16, 64, True, 5),
     ("single_C_n4", "C", "minus", "single", 0.2, 4, 4, 16, 32, False, 6),
-    ("dual_B_n1x2", "B", "multiply", "dual", 0.2, 1, 2, 16, 32, True, 7),
+    ("dual_B_n1x1", "B", "multiply", "dual", 0.2, 1, 1, 16, 32, True, 7),
     ("dualmax_A_n3x7", "A", "minus_abs", "dual_max", 0.2, 3, 7, 20, 32, True, 8),
 ]
 
