@@ -82,7 +82,15 @@ enum mmmot_weight_id {
   MMMOT_W_NE_W1T = 129, MMMOT_W_NE_B1 = 130, MMMOT_W_NE_G1W = 131, MMMOT_W_NE_G1B = 132,
   MMMOT_W_NE_W2T = 133, MMMOT_W_NE_B2 = 134, MMMOT_W_NE_G2W = 135, MMMOT_W_NE_G2B = 136,
   MMMOT_W_NE_W3 = 137, MMMOT_W_NE_B3 = 138,
-  MMMOT_W_COUNT = 139
+  /* ---- tensor-core operands: the same matrices split into BF16 hi/lo and pre-tiled in the UMMA
+     canonical K-major core-matrix layout  [k chunk 32][m tile 128][hi|lo][k group 4][m group 16][8][8]
+     (zero padded to multiples of 128 rows / 32 k); see csrc/gemm_tc.cuh.  VGG rows use the K order
+     k = ci*9 + (ky*3+kx). */
+  MMMOT_W_VGG_WP0 = 139,          /* .. +12 */
+  MMMOT_W_PN_WP1 = 152,           /* .. +4 : PointNet trunk layers 1..5 (slot of layer 1 unused) */
+  MMMOT_W_PN_WHAP = 157,
+  MMMOT_W_AF_W01P = 158, MMMOT_W_AF_W2P = 159, MMMOT_W_AF_W3P = 160,
+  MMMOT_W_COUNT = 161
 };
 
 typedef struct mmmot_weights {
@@ -160,6 +168,16 @@ int mmmot_lp_assign(const float* det, long det_stride, const float* link, long l
                     int pairs, int n, int m,
                     float* a_det, float* a_link, float* a_new, float* a_end, int* match,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Contraction engine selection: 0 = auto (tcgen05 tensor-core engine for large problems, FP32 FFMA
+ * engine for tiny ones), 1 = force the FP32 FFMA engine, 2 = force the tcgen05 engine.  Both engines
+ * implement the same contraction; the switch exists for A/B parity tests and profiling. */
+int mmmot_set_engine(int engine);
+
+/* Test hook: Y[M][S] = W X + bias through one engine (1 = FP32 FFMA, 2 = tcgen05); Wt is [K][M] fp32,
+ * Wp the packed BF16 hi/lo tiles of the same matrix, X is [K][S], all device pointers. */
+int mmmot_debug_linear(const float* Wt, const void* Wp, const float* bias, const float* X, float* Y,
+                       int M, int K, int S, int engine, void* stream);
 
 /* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
  * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed

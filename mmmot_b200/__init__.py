@@ -3,3 +3,10 @@ forward behind the reference's own Python surface.  See DESIGN.md."""
 from .config import build_model, model_kwargs  # noqa: F401
 from .solvers import ortools_solve, solve_batch  # noqa: F401
 from .tracking_net import TrackingNet  # noqa: F401
+
+
+def set_engine(engine):
+    """Contraction engine: "auto" (default), "fp32" (FFMA engine) or "tcgen05" (tensor-core engine)."""
+    from . import _lib
+    code = {"auto": 0, "fp32": 1, "tcgen05": 2}[engine]
+    _lib.check(_lib.load().mmmot_set_engine(code), "mmmot_set_engine")

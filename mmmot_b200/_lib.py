@@ -26,7 +26,8 @@ W = dict(
     AF_W2T=119, AF_B2=120, AF_G2W=121, AF_G2B=122, AF_W3T=123, AF_B3=124, AF_G3W=125, AF_G3B=126,
     AF_W4=127, AF_B4=128,
     NE_W1T=129, NE_B1=130, NE_G1W=131, NE_G1B=132, NE_W2T=133, NE_B2=134, NE_G2W=135, NE_G2B=136,
-    NE_W3=137, NE_B3=138, COUNT=139,
+    NE_W3=137, NE_B3=138,
+    VGG_WP0=139, PN_WP1=152, PN_WHAP=157, AF_W01P=158, AF_W2P=159, AF_W3P=160, COUNT=161,
 )
 
 
@@ -46,6 +47,8 @@ SIGNATURES = {
     "mmmot_abi_version": (_i, []),
     "mmmot_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "mmmot_launch_count": (ctypes.c_ulonglong, []),
+    "mmmot_set_engine": (_i, [_i]),
+    "mmmot_debug_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mmmot_timing_enable": (_i, [_i]),
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),

@@ -6,7 +6,7 @@
 // 100.7 MB per pair at N=M=128) is generated inside the first contraction's operand loader and
 // never exists in HBM; affinity conv1.0 and new/end conv0 (both 512->512 on the same x) run as
 // ONE 512->1024 contraction.
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "norm_ops.cuh"
 
 namespace {
@@ -178,7 +178,9 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
 }
 
 template <int MODE>
-int first_layer(GemmP& p, cudaStream_t st) { return gemm_simt_launch<MODE>(p, st); }
+int run_layer(GemmP& p, const void* wp, bool use_tc, cudaStream_t st) {
+  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wp, st) : gemm_simt_launch<MODE>(p, st);
+}
 
 }  // namespace
 
@@ -200,7 +202,8 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   AfWs w = carve(ar, pairs, n, m);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
   const int G = pairs * 3, NM = n * m, L = n + m;
-  const int tpg = mm_cdiv(NM, 128);
+  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && (long)G * NM >= 4096);
+  const int tpg = mm_cdiv(NM, use_tc ? tc::BN : 128);
   const float* const* W = wts->w;
 
   // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor
@@ -211,9 +214,10 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     p.X = feats; p.n = n; p.m = m; p.Lf = L;
     p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
     p.part = w.part;
-    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? first_layer<XM_PAIR_MUL>(p, st)
-            : affinity_op == MMMOT_AFF_MINUS_ABS ? first_layer<XM_PAIR_ABS>(p, st)
-                                                 : first_layer<XM_PAIR_SUB>(p, st);
+    const void* wp = W[MMMOT_W_AF_W01P];
+    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wp, use_tc, st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wp, use_tc, st)
+                                                 : run_layer<XM_PAIR_SUB>(p, wp, use_tc, st);
     if (r) return r;
   }
   // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),
@@ -259,13 +263,13 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     p.X = w.y01; p.x_gs = 1024L * NM; p.x_ks = NM; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.y2; p.y_gs = 512L * NM; p.y_ms = NM;
     p.part = w.part;
-    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(run_layer<XM_NORM_RELU>(p, W[MMMOT_W_AF_W2P], use_tc, st));
     MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
     p.Wt = W[MMMOT_W_AF_W3T]; p.bias = W[MMMOT_W_AF_B3]; p.ldw = 128; p.M = 128;
     p.X = w.y2; p.x_gs = 512L * NM; p.sc = w.sc2; p.sh = w.sh2;
     p.Y = w.y3; p.y_gs = 128L * NM;
-    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(run_layer<XM_NORM_RELU>(p, W[MMMOT_W_AF_W3P], use_tc, st));
     MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   }

@@ -78,3 +78,34 @@ extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* 
   if (launches) *launches = n;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Engine selection + single-contraction test hook.
+#include "gemm_tc.cuh"
+
+namespace { int g_engine = 0; }
+
+int mm_engine() { return g_engine; }
+
+extern "C" int mmmot_set_engine(int engine) {
+  if (engine < 0 || engine > 2) return MMMOT_E_ARG;
+  g_engine = engine;
+  return 0;
+}
+
+extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, const float* bias, const float* X, float* Y,
+                                  int M, int K, int S, int engine, void* stream) {
+  if (!Wt || !X || !Y || M <= 0 || K <= 0 || S <= 0) return MMMOT_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmP p = gemm_defaults();
+  p.Wt = Wt; p.ldw = M; p.bias = bias; p.M = M; p.K = K;
+  p.S = S;
+  p.X = X; p.x_ks = S;
+  p.Y = Y; p.y_ms = S;
+  if (engine == 2) {
+    p.tiles_per_group = mm_cdiv(S, tc::BN); p.num_tiles = p.tiles_per_group;
+    return gemm_tc_launch<XM_DIRECT>(p, (const uint4*)Wp, st);
+  }
+  p.tiles_per_group = mm_cdiv(S, 128); p.num_tiles = p.tiles_per_group;
+  return gemm_simt_launch<XM_DIRECT>(p, st);
+}

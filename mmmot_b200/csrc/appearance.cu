@@ -1,6 +1,6 @@
 // Appearance branch: VGG16-BN trunk (BN folded) + 4 SkipPool heads.
 // Replaces reference modules/appear_net.py:166-190 (vgg_forward + SkipPool.forward :27-32).
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace {
 
@@ -131,14 +131,17 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     p.Cin = kVggCin[i];
     p.H = h; p.W = w;
     p.S = n_img * h * w;
-    p.tiles_per_group = mm_cdiv(p.S, 128);
-    p.num_tiles = p.tiles_per_group;
     p.X = cur;
     p.Y = buf[which];
     p.relu = 1;
+    // tensor-core engine for every layer with enough columns to fill the machine
+    const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && p.S >= 4096);
+    p.tiles_per_group = mm_cdiv(p.S, use_tc ? tc::BN : 128);
+    p.num_tiles = p.tiles_per_group;
     const bool timed = mm_timing_on();
     if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
-    MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
+    if (use_tc) MM_TRY(gemm_tc_launch<XM_CONV3>(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], st));
+    else MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
     if (timed) mm_timing_end(st);
     cur = buf[which]; which ^= 1;
     if (kPoolAfter[i]) {

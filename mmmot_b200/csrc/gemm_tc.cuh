@@ -1,0 +1,427 @@
+// tcgen05 contraction engine (sm_100a):  Y[g][co][s] = sum_k W[co][k] * Xin(g,k,s) + bias[co]
+//
+// Same operand generators and fused epilogue as the FP32 engine in gemm_simt.cuh, but the
+// contraction runs on the 5th-gen tensor cores with FP32-grade accuracy by splitting every FP32
+// operand into two BF16 terms, x = hi + lo (|x - hi - lo| <= 2^-17 |x|), and issuing three BF16
+// MMAs per k-step:  D += Ahi*Bhi + Ahi*Blo + Alo*Bhi   (the dropped lo*lo term is <= 2^-18 relative).
+// Single-pass TF32 / BF16 operands miss the 1e-4 parity bound; this does not.
+//
+// Persistent, warp-specialised CTA (one per SM), tile 256 (M) x 256 (N), K chunks of 32:
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = output channel), bias / addend /
+//               ReLU, per-thread GroupNorm partial sums (no shuffles), 128-bit stores
+//   warp  4     MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16), 12 per
+//               chunk; accumulators (2 x 256 fp32 columns) live in TMEM; owns TMEM alloc/dealloc
+//   warp  5     A loader: one thread, cp.async.bulk (TMA engine, no tensor map) of pre-packed
+//               BF16 hi/lo weight tiles, completion on the stage's mbarrier
+//   warps 6-13  B producers: generate the operand tile (plain load / GroupNorm+ReLU of the
+//               producer layer / pairwise op / 3x3 im2col), split to BF16 hi/lo and write it to
+//               shared memory in the UMMA canonical K-major (no-swizzle) core-matrix layout
+// 3-stage smem ring (64 KB per stage), mbarrier full/empty pipeline, tcgen05.commit releases stages.
+#pragma once
+#include "gemm_simt.cuh"
+
+namespace tc {
+
+constexpr int BN = 256;            // columns per tile
+constexpr int BK = 32;             // K per pipeline stage
+constexpr int STAGES = 3;
+constexpr int A_HALF = 128 * BK * 2;          // one 128-row subtile, hi or lo (8 KB)
+constexpr int A_SUB = 2 * A_HALF;             // hi | lo
+constexpr int B_HALF = BN * BK * 2;           // 16 KB
+constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_HALF;   // 64 KB
+constexpr int A_LBO = 16 * 128, B_LBO = 32 * 128, SBO = 128;
+constexpr int NUM_THREADS = 448;
+constexpr int PRODUCER_T0 = 192;   // first producer thread
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, BF16 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no-swizzle canonical layout: 8x(16 B) core matrices; LBO = stride between the two K
+// core matrices of one k-step, SBO = stride between 8-row groups (cute/atom/mma_traits_sm100.hpp
+// make_umma_desc<Major::K>, LayoutType::INTERLEAVE).  version = 1 (Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=256
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x0 (low half-word) , x1 (high half-word) -> packed bf16x2, round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16x2(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+
+struct TcP {
+  GemmP g;             // same fields as the FP32 engine (tile width is tc::BN here)
+  const uint4* Wp;     // packed weights: [kchunk][m128 tile][hi|lo][kgroup 4][m8 16][8 rows][8 k] bf16
+  int m_tiles;         // ceil(M / 128) (packed rows beyond M are zero)
+  int k_chunks;        // ceil(K / 32)
+  int mt_per_cta;      // 1 or 2 (128-row subtiles per CTA tile)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
+  const GemmP& p = P.g;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[3], empty[3], tmem_full, tmem_empty ; then tmem base (4 B)
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES), tempty_bar = bar0 + 8u * (2 * STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = P.mt_per_cta;
+  const int mgroups = (P.m_tiles + MT - 1) / MT;
+  const long total_tiles = (long)p.num_tiles * mgroups;
+  const int KC = P.k_chunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar(s), 9);   // 8 producer warps + the A loader's expect_tx arrive
+      mbar_init(empty_bar(s), 1);  // tcgen05.commit
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =============================== EPILOGUE ===============================
+    uint32_t tphase = 0;
+    const int hw = (MODE == XM_CONV3) ? p.H * p.W : 1;
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mg = (int)(t % mgroups);
+      const int nt = (int)(t / mgroups);
+      int g, c0, len;
+      if (p.tile_tab) { int4 tt = p.tile_tab[nt]; g = tt.x; c0 = tt.y; len = tt.z; }
+      else { g = nt / p.tiles_per_group; c0 = (nt - g * p.tiles_per_group) * BN; len = min(BN, p.S - c0); }
+      mbar_wait(tfull_bar, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+      for (int mt = 0; mt < MT; mt++) {
+        const int co = (mg * MT + mt) * 128 + warp * 32 + lane;
+        const bool rowok = co < p.M;
+        const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
+        double d1 = 0.0, d2 = 0.0;
+        float* rowp = nullptr;
+        if (MODE != XM_CONV3 && p.Y && rowok) rowp = p.Y + (long)g * p.y_gs + (long)co * p.y_ms + c0;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; cc++) {
+          if (cc * 32 >= len) break;   // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 256 + cc * 32), v);
+          if (!rowok) continue;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float x = __uint_as_float(v[j]) + bv;
+            const int col = cc * 32 + j;
+            if (p.addend && col < len) x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
+            if (p.relu) x = fmaxf(x, 0.f);
+            v[j] = __float_as_uint(x);
+            if (col < len) { s1 += x; s2 += x * x; }
+          }
+          d1 += (double)s1; d2 += (double)s2;
+          if (p.Y) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int col = cc * 32 + q * 4;
+              if (col >= len) break;
+              float* dst;
+              bool vec;
+              if (MODE == XM_CONV3) {
+                const int s = c0 + col;
+                const int img = s / hw, pix = s - img * hw;
+                dst = p.Y + ((long)img * p.M + co) * hw + pix;
+                vec = ((hw & 3) == 0) && (col + 3 < len);
+              } else {
+                dst = rowp + col;
+                vec = (col + 3 < len) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+              }
+              if (vec) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              } else {
+                for (int e = 0; e < 4; e++) {
+                  if (col + e >= len) break;
+                  if (MODE == XM_CONV3) {
+                    const int s = c0 + col + e;
+                    const int img = s / hw, pix = s - img * hw;
+                    p.Y[((long)img * p.M + co) * hw + pix] = __uint_as_float(v[q * 4 + e]);
+                  } else {
+                    dst[e] = __uint_as_float(v[q * 4 + e]);
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (p.part && rowok) p.part[(long)nt * p.M + co] = make_double2(d1, d2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+  } else if (warp == 4) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, tcount++) {
+        mbar_wait(tempty_bar, (tcount & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < KC; kc++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_SUB;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            if (mt < MT) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++) {
+                const uint64_t a_hi = smem_desc(sa + mt * A_SUB + ks * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t a_lo = smem_desc(sa + mt * A_SUB + A_HALF + ks * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t b_hi = smem_desc(sb + ks * 2 * B_LBO, B_LBO, SBO);
+                const uint64_t b_lo = smem_desc(sb + B_HALF + ks * 2 * B_LBO, B_LBO, SBO);
+                const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+                umma_bf16(d, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
+                umma_bf16(d, a_hi, b_lo, IDESC, 1u);
+                umma_bf16(d, a_lo, b_hi, IDESC, 1u);
+              }
+            }
+          }
+          umma_commit(empty_bar(s));                 // stage free once these MMAs have read it
+          if (kc == KC - 1) umma_commit(tfull_bar);  // accumulators complete
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =============================== A LOADER ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mg = (int)(t % mgroups);
+        const int mt0 = mg * MT;
+        const int nmt = min(MT, P.m_tiles - mt0);
+        for (int kc = 0; kc < KC; kc++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          const uint32_t bytes = (uint32_t)nmt * A_SUB;
+          mbar_expect_tx(full_bar(s), bytes);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(P.Wp) + ((size_t)kc * P.m_tiles + mt0) * A_SUB;
+          bulk_g2s(base + s * STAGE_BYTES, src, bytes, full_bar(s));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== B PRODUCERS ===============================
+    const int col = tid - PRODUCER_T0;  // 0..255: this thread's column of the tile
+    uint32_t it = 0;
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = (int)(t / mgroups);
+      int g, c0, len;
+      if (p.tile_tab) { int4 tt = p.tile_tab[nt]; g = tt.x; c0 = tt.y; len = tt.z; }
+      else { g = nt / p.tiles_per_group; c0 = (nt - g * p.tiles_per_group) * BN; len = min(BN, p.S - c0); }
+      const bool colok = col < len;
+      long coff = 0;
+      int aux = 0, pi = 0;
+      if (MODE == XM_DIRECT || MODE == XM_NORM_RELU) {
+        coff = (long)g * p.x_gs + c0 + col;
+      } else if (MODE == XM_CONV3) {
+        const int s = c0 + col, hw = p.H * p.W;
+        const int img = s / hw, pix = s - img * hw;
+        const int y = pix / p.W, x = pix - y * p.W;
+        coff = (long)img * p.Cin * hw + pix;
+#pragma unroll
+        for (int tp = 0; tp < 9; tp++) {
+          const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) aux |= 1 << tp;
+        }
+        if (!colok) aux = 0;
+      } else {
+        const int s = c0 + col;
+        pi = s / p.m;
+        aux = p.n + (s - pi * p.m);
+      }
+      const uint32_t row_off = (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;
+
+      for (int kc = 0; kc < KC; kc++, it++) {
+        const int s = it % STAGES;
+        const int k0 = kc * BK;
+        float v[BK];
+        // ---- gather (global loads issued before waiting for the smem slot) ----
+        if (MODE == XM_DIRECT || MODE == XM_NORM_RELU) {
+#pragma unroll
+          for (int e = 0; e < BK; e++) {
+            const int k = k0 + e;
+            float x = 0.f;
+            if (colok && k < p.K) {
+              x = __ldg(p.X + coff + (long)k * p.x_ks);
+              if (MODE == XM_NORM_RELU)
+                x = fmaxf(fmaf(x, __ldg(p.sc + (long)g * p.K + k), __ldg(p.sh + (long)g * p.K + k)), 0.f);
+            }
+            v[e] = x;
+          }
+        } else if (MODE == XM_CONV3) {
+          // K order: k = ci*9 + tap (the 9 taps of one input plane are adjacent -> L1 reuse)
+          int ci = k0 / 9, tap = k0 - ci * 9;
+          const int hw = p.H * p.W;
+#pragma unroll
+          for (int e = 0; e < BK; e++) {
+            float x = 0.f;
+            if (ci < p.Cin && ((aux >> tap) & 1)) {
+              const int d = (tap / 3 - 1) * p.W + (tap % 3 - 1);
+              x = __ldg(p.X + coff + (long)ci * hw + d);
+            }
+            v[e] = x;
+            if (++tap == 9) { tap = 0; ci++; }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < BK; e++) {
+            const int k = k0 + e;
+            float x = 0.f;
+            if (colok && k < p.K) {
+              const float* fr = p.X + ((long)g * p.K + k) * p.Lf;
+              const float a = __ldg(fr + pi), b = __ldg(fr + aux);
+              if (MODE == XM_PAIR_MUL) x = a * b;
+              else if (MODE == XM_PAIR_ABS) x = fabsf((a - b) * 0.5f);
+              else x = (a - b) * 0.5f;
+            }
+            v[e] = x;
+          }
+        }
+        // ---- split to bf16 hi / lo and publish in the canonical layout ----
+        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+        uint8_t* bh = sm + s * STAGE_BYTES + 2 * A_SUB;
+#pragma unroll
+        for (int kg = 0; kg < BK / 8; kg++) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float x0 = v[kg * 8 + 2 * q], x1 = v[kg * 8 + 2 * q + 1];
+            const uint32_t hh = pack_bf16x2(x0, x1);
+            const float r0 = x0 - __uint_as_float(hh << 16), r1 = x1 - __uint_as_float(hh & 0xffff0000u);
+            h[q] = hh;
+            l[q] = pack_bf16x2(r0, r1);
+          }
+          *reinterpret_cast<uint4*>(bh + kg * B_LBO + row_off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(bh + B_HALF + kg * B_LBO + row_off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// Host launcher.  `Wp` = weights packed by mmmot_b200/weights.py::pack_tc.
+template <int MODE>
+static int gemm_tc_launch(const GemmP& g, const uint4* Wp, cudaStream_t st) {
+  if (!Wp || g.num_tiles <= 0) return MMMOT_E_ARG;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    MM_CUDA(cudaGetDevice(&dev));
+    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(tc::gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  tc::TcP P;
+  P.g = g;
+  P.Wp = Wp;
+  P.m_tiles = (g.M + 127) / 128;
+  P.k_chunks = (g.K + tc::BK - 1) / tc::BK;
+  P.mt_per_cta = P.m_tiles >= 2 ? 2 : 1;
+  const long mgroups = (P.m_tiles + P.mt_per_cta - 1) / P.mt_per_cta;
+  const long total = (long)g.num_tiles * mgroups;
+  const int grid = (int)(total < sms ? total : sms);
+  tc::gemm_tc_kernel<MODE><<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(P);
+  MM_LAUNCH_CHECK();
+  return 0;
+}

@@ -8,7 +8,7 @@
 // Per-detection pooling is a MEAN.  One frame-pair = one GroupNorm domain.
 #include <vector>
 
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "norm_ops.cuh"
 
 namespace {
@@ -120,13 +120,15 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     if (h_det_split[d + 1] <= h_det_split[d]) return MMMOT_E_SHAPE;  // every detection owns >= 1 point
 
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
+  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && P >= 4096);
+  const int TNW = use_tc ? tc::BN : 128;
   std::vector<int4> tiles;
   std::vector<int> cnt(pairs), gstart(pairs + 1);
   for (int p = 0; p < pairs; p++) {
     int s = h_det_split[p * L], e = h_det_split[(p + 1) * L];
     cnt[p] = e - s;
     gstart[p] = (int)tiles.size();
-    for (int c = s; c < e; c += 128) tiles.push_back(make_int4(p, c, min(128, e - c), 0));
+    for (int c = s; c < e; c += TNW) tiles.push_back(make_int4(p, c, min(TNW, e - c), 0));
   }
   gstart[pairs] = (int)tiles.size();
   const long max_tiles = P / 128 + pairs + 1;
@@ -154,12 +156,15 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.X = src[i]; p.x_ks = P;
     p.Y = dst[i]; p.y_ms = P;
     p.part = w.part;
+    const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
     if (i == 0) {
-      MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+      if (use_tc) MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, st));
+      else MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
     } else {
       p.sc = (i == 1) ? w.sc1 : w.sc;
       p.sh = (i == 1) ? w.sh1 : w.sh;
-      MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+      if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, wp, st));
+      else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     }
     MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, i == 0 ? w.sc1 : w.sc,
@@ -187,7 +192,8 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.Y = w.big; p.y_ms = P;
     p.part = w.part;
     p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
-    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], st));
+    else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,
                        w.sc, w.sh, st));

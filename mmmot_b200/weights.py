@@ -43,6 +43,22 @@ def _fold_bn(sd, conv, bn):
     return w, b
 
 
+def pack_tc(wt):
+    """Wt[K][M] (fp32/fp64) -> uint8 tensor holding the tcgen05 operand tiles of W = Wt^T:
+    [k chunk 32][m tile 128][hi|lo][k group 4][m group 16][8 rows][8 k] bf16, zero padded.
+    hi = bf16(w) (round-to-nearest-even), lo = bf16(w - hi): w = hi + lo to 2^-17 relative."""
+    w = wt.t().float().contiguous()                       # [M][K]
+    M, K = w.shape
+    mt, kc = (M + 127) // 128, (K + 31) // 32
+    pad = torch.zeros(mt * 128, kc * 32, dtype=torch.float32)
+    pad[:M, :K] = w
+    hi = pad.to(torch.bfloat16)
+    lo = (pad - hi.float()).to(torch.bfloat16)
+    both = torch.stack([hi, lo], 0).view(2, mt, 16, 8, kc, 4, 8)      # hl, mt, mg, r, kc, kg, e
+    both = both.permute(4, 1, 0, 5, 2, 3, 6).contiguous()              # kc, mt, hl, kg, mg, r, e
+    return both.view(torch.int16).reshape(-1).view(torch.uint8)
+
+
 def prepare(state_dict, fusion):
     """-> (list of fp32 CPU tensors indexed by weight id (None = unused), trans1 3x3, trans2 64x64)."""
     sd = {k: v.detach().cpu() for k, v in state_dict.items()}
@@ -132,6 +148,20 @@ def prepare(state_dict, fusion):
     out[W["NE_W3"]] = f64(f"{ne}.6.weight").reshape(-1); out[W["NE_B3"]] = f64(f"{ne}.6.bias")
 
     out = [None if t is None else t.contiguous().float() for t in out]
+    # tensor-core operand tiles (bytes, viewed as float32 words for the flat buffer)
+    i = 0
+    for s_, stage in enumerate(VGG_STAGES):
+        for idx, cin, cout in stage:
+            w, _ = _fold_bn(sd, f"appearance.layers.{s_}.{idx}", f"appearance.layers.{s_}.{idx + 1}")
+            out[W["VGG_WP0"] + i] = pack_tc(w.reshape(cout, cin * 9).t())        # K order ci*9 + tap
+            i += 1
+    for j in range(1, 5):
+        out[W["PN_WP1"] + j] = pack_tc(out[W["PN_L1"] + 4 * j])
+    out[W["PN_WHAP"]] = pack_tc(out[W["PN_WHAT"]])
+    out[W["AF_W01P"]] = pack_tc(out[W["AF_W01T"]])
+    out[W["AF_W2P"]] = pack_tc(out[W["AF_W2T"]])
+    out[W["AF_W3P"]] = pack_tc(out[W["AF_W3T"]])
+    out = [t.view(torch.float32) if (t is not None and t.dtype == torch.uint8) else t for t in out]
     return out, t1.float(), t2.float()
 
 

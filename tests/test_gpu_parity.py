@@ -21,8 +21,35 @@ def make_net(fusion, op, sm, thr, seed):
     return net.cuda().eval(), sd
 
 
+@pytest.fixture(params=["fp32", "tcgen05"])
+def engine(request):
+    """Both contraction engines must meet the same parity bound."""
+    mmmot_b200.set_engine(request.param)
+    yield request.param
+    mmmot_b200.set_engine("auto")
+
+
+@pytest.mark.parametrize("M,K,S", [(128, 32, 256), (256, 96, 512), (64, 70, 300), (512, 512, 4099), (1024, 128, 1000),
+                                   (128, 4608, 2048)])
+def test_tcgen05_contraction_vs_fp64(M, K, S):
+    """The split-BF16 tensor-core contraction alone (C ABI test hook) against an fp64 matmul."""
+    import ctypes
+    from mmmot_b200 import _lib
+    from mmmot_b200.weights import pack_tc
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + K + S)
+    Wt, X, b = torch.randn(K, M, generator=g), torch.randn(K, S, generator=g), torch.randn(M, generator=g)
+    ref = Wt.double().t() @ X.double() + b.double()[:, None]
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    Wt_d, X_d, b_d, Wp = Wt.cuda(), X.cuda(), b.cuda(), pack_tc(Wt).cuda()
+    for eng in (1, 2):
+        Y = torch.full((M, S), float("nan"), device="cuda")
+        assert lib.mmmot_debug_linear(vp(Wt_d), vp(Wp), vp(b_d), vp(X_d), vp(Y), M, K, S, eng, None) == 0
+        assert relerr(Y, ref) < 3e-5, eng
+
+
 @pytest.mark.parametrize("g", CASES, ids=[c["case"][0] for c in CASES])
-def test_forward_matches_reference_golden(g):
+def test_forward_matches_reference_golden(g, engine):
     """Reference signature, one frame-pair, against outputs of the UNMODIFIED reference."""
     name, fusion, op, sm, thr, n, m, pts, hw, ragged, seed = g["case"]
     net, sd = make_net(fusion, op, sm, thr, seed)
@@ -38,7 +65,7 @@ def test_forward_matches_reference_golden(g):
 
 
 @pytest.mark.parametrize("fusion,op,sm", [("A", "multiply", "none"), ("C", "minus_abs", "dual_add"), ("B", "multiply", "none")])
-def test_features_match_oracle(fusion, op, sm):
+def test_features_match_oracle(fusion, op, sm, engine):
     """Stage check: the 3x512xL feature stack (appearance | PointNet | fusion), N=M=16, 64x64 crops."""
     net, sd = make_net(fusion, op, sm, 0.2, 31)
     dets, info, split = synthetic_pair(16, 16, 48, 64, seed=31, ragged=True)
@@ -50,7 +77,7 @@ def test_features_match_oracle(fusion, op, sm):
 
 @pytest.mark.parametrize("n,m", [(8, 8), (32, 32), (64, 64), (20, 45), (128, 128)])
 @pytest.mark.parametrize("op,sm", [("multiply", "none"), ("minus_abs", "dual_add")])
-def test_affinity_stage_matches_oracle(n, m, op, sm):
+def test_affinity_stage_matches_oracle(n, m, op, sm, engine):
     """BASELINE config 5 (N sweep): affinity + start/end + softmax alone on identical feature tensors."""
     net, sd = make_net("C", op, sm, 0.2, 7)
     g = torch.Generator().manual_seed(n * 1000 + m)
