@@ -82,12 +82,12 @@ enum mmmot_weight_id {
   MMMOT_W_NE_W1T = 129, MMMOT_W_NE_B1 = 130, MMMOT_W_NE_G1W = 131, MMMOT_W_NE_G1B = 132,
   MMMOT_W_NE_W2T = 133, MMMOT_W_NE_B2 = 134, MMMOT_W_NE_G2W = 135, MMMOT_W_NE_G2B = 136,
   MMMOT_W_NE_W3 = 137, MMMOT_W_NE_B3 = 138,
-  /* ---- tensor-core operands: the same matrices split into BF16 hi/lo and pre-tiled in the UMMA
+  /* ---- tensor-core operands: the same matrices split into FP16 hi/lo and pre-tiled in the UMMA
      canonical K-major core-matrix layout  [k chunk 32][m tile 128][hi|lo][k group 4][m group 16][8][8]
-     (zero padded to multiples of 128 rows / 32 k); see csrc/gemm_tc.cuh.  VGG rows use the K order
-     k = ci*9 + (ky*3+kx). */
+     (zero padded to multiples of 128 rows / 32 k); see csrc/gemm_tc.cuh.  VGG layer 0 (fp32 NCHW crops) uses
+     the K order k = ci*9 + (ky*3+kx); layers 1..12 (packed FP16 NHWC activations) use k = (ky*3+kx)*Cin + ci. */
   MMMOT_W_VGG_WP0 = 139,          /* .. +12 */
-  MMMOT_W_PN_WP1 = 152,           /* .. +4 : PointNet trunk layers 1..5 (slot of layer 1 unused) */
+  MMMOT_W_PN_WP1 = 152,           /* .. +4 : PointNet trunk layers 1..5 */
   MMMOT_W_PN_WHAP = 157,
   MMMOT_W_AF_W01P = 158, MMMOT_W_AF_W2P = 159, MMMOT_W_AF_W3P = 160,
   MMMOT_W_COUNT = 161
@@ -95,6 +95,9 @@ enum mmmot_weight_id {
 
 typedef struct mmmot_weights {
   const float* w[MMMOT_W_COUNT];
+  /* for the packed tensor-core operands (ids >= MMMOT_W_VGG_WP0): 2^-s, where the packed FP16 tiles
+     hold W * 2^s (power-of-two pre-scaling keeps the lo terms in FP16's normal range) */
+  float tc_scale[MMMOT_W_COUNT];
 } mmmot_weights;
 
 int mmmot_abi_version(void);
@@ -174,10 +177,14 @@ int mmmot_lp_assign(const float* det, long det_stride, const float* link, long l
  * implement the same contraction; the switch exists for A/B parity tests and profiling. */
 int mmmot_set_engine(int engine);
 
+/* Profiling experiments on the tcgen05 engine (bit 0 skip epilogue work, 1 skip weight loads, 2 skip
+ * operand generation, 3 skip MMA issue); results are WRONG with any bit set.  Default 0. */
+int mmmot_set_debug(int flags);
+
 /* Test hook: Y[M][S] = W X + bias through one engine (1 = FP32 FFMA, 2 = tcgen05); Wt is [K][M] fp32,
- * Wp the packed BF16 hi/lo tiles of the same matrix, X is [K][S], all device pointers. */
-int mmmot_debug_linear(const float* Wt, const void* Wp, const float* bias, const float* X, float* Y,
-                       int M, int K, int S, int engine, void* stream);
+ * Wp the packed FP16 hi/lo tiles of the same matrix (wp_scale = its 2^-s), X is [K][S], all device pointers. */
+int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const float* bias, const float* X,
+                       float* Y, int M, int K, int S, int engine, void* stream);
 
 /* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
  * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed

@@ -32,7 +32,7 @@ W = dict(
 
 
 class Weights(ctypes.Structure):
-    _fields_ = [("w", ctypes.c_void_p * W["COUNT"])]
+    _fields_ = [("w", ctypes.c_void_p * W["COUNT"]), ("tc_scale", ctypes.c_float * W["COUNT"])]
 
 
 class MmmotError(RuntimeError):
@@ -48,7 +48,8 @@ SIGNATURES = {
     "mmmot_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "mmmot_launch_count": (ctypes.c_ulonglong, []),
     "mmmot_set_engine": (_i, [_i]),
-    "mmmot_debug_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mmmot_set_debug": (_i, [_i]),
+    "mmmot_debug_linear": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mmmot_timing_enable": (_i, [_i]),
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),

@@ -178,8 +178,8 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
 }
 
 template <int MODE>
-int run_layer(GemmP& p, const void* wp, bool use_tc, cudaStream_t st) {
-  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wp, st) : gemm_simt_launch<MODE>(p, st);
+int run_layer(GemmP& p, const mmmot_weights* wts, int wid, bool use_tc, cudaStream_t st) {
+  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wts->w[wid], wts->tc_scale[wid], st) : gemm_simt_launch<MODE>(p, st);
 }
 
 }  // namespace
@@ -214,10 +214,9 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     p.X = feats; p.n = n; p.m = m; p.Lf = L;
     p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
     p.part = w.part;
-    const void* wp = W[MMMOT_W_AF_W01P];
-    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wp, use_tc, st)
-            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wp, use_tc, st)
-                                                 : run_layer<XM_PAIR_SUB>(p, wp, use_tc, st);
+    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wts, MMMOT_W_AF_W01P, use_tc, st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wts, MMMOT_W_AF_W01P, use_tc, st)
+                                                 : run_layer<XM_PAIR_SUB>(p, wts, MMMOT_W_AF_W01P, use_tc, st);
     if (r) return r;
   }
   // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),
@@ -263,13 +262,13 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     p.X = w.y01; p.x_gs = 1024L * NM; p.x_ks = NM; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.y2; p.y_gs = 512L * NM; p.y_ms = NM;
     p.part = w.part;
-    MM_TRY(run_layer<XM_NORM_RELU>(p, W[MMMOT_W_AF_W2P], use_tc, st));
+    MM_TRY(run_layer<XM_NORM_RELU>(p, wts, MMMOT_W_AF_W2P, use_tc, st));
     MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
     p.Wt = W[MMMOT_W_AF_W3T]; p.bias = W[MMMOT_W_AF_B3]; p.ldw = 128; p.M = 128;
     p.X = w.y2; p.x_gs = 512L * NM; p.sc = w.sc2; p.sh = w.sh2;
     p.Y = w.y3; p.y_gs = 128L * NM;
-    MM_TRY(run_layer<XM_NORM_RELU>(p, W[MMMOT_W_AF_W3P], use_tc, st));
+    MM_TRY(run_layer<XM_NORM_RELU>(p, wts, MMMOT_W_AF_W3P, use_tc, st));
     MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   }

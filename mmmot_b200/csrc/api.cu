@@ -83,7 +83,9 @@ extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* 
 // Engine selection + single-contraction test hook.
 #include "gemm_tc.cuh"
 
-namespace { int g_engine = 0; }
+namespace { int g_engine = 0; int g_dbg = 0; }
+int mm_debug_flags() { return g_dbg; }
+extern "C" int mmmot_set_debug(int flags) { g_dbg = flags; return 0; }
 
 int mm_engine() { return g_engine; }
 
@@ -93,8 +95,8 @@ extern "C" int mmmot_set_engine(int engine) {
   return 0;
 }
 
-extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, const float* bias, const float* X, float* Y,
-                                  int M, int K, int S, int engine, void* stream) {
+extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const float* bias, const float* X,
+                                  float* Y, int M, int K, int S, int engine, void* stream) {
   if (!Wt || !X || !Y || M <= 0 || K <= 0 || S <= 0) return MMMOT_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   GemmP p = gemm_defaults();
@@ -104,7 +106,7 @@ extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, const float* 
   p.Y = Y; p.y_ms = S;
   if (engine == 2) {
     p.tiles_per_group = mm_cdiv(S, tc::BN); p.num_tiles = p.tiles_per_group;
-    return gemm_tc_launch<XM_DIRECT>(p, (const uint4*)Wp, st);
+    return gemm_tc_launch<XM_DIRECT>(p, (const uint4*)Wp, wp_scale, st);
   }
   p.tiles_per_group = mm_cdiv(S, 128); p.num_tiles = p.tiles_per_group;
   return gemm_simt_launch<XM_DIRECT>(p, st);

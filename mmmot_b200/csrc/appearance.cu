@@ -1,5 +1,7 @@
 // Appearance branch: VGG16-BN trunk (BN folded) + 4 SkipPool heads.
 // Replaces reference modules/appear_net.py:166-190 (vgg_forward + SkipPool.forward :27-32).
+#include <cuda_fp16.h>
+
 #include "gemm_tc.cuh"
 
 namespace {
@@ -40,6 +42,46 @@ __global__ void plane_mean_kernel(const float* __restrict__ in, float* __restric
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[w] = s / (float)hw;
+}
+
+// ---- packed FP16 (hi | lo << 16) NHWC activations of the tensor-core trunk ----
+__device__ __forceinline__ float unpack_split(uint32_t w) {
+  return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))) +
+         __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+
+// 2x2 / stride 2 max-pool on packed NHWC words: the max IS one of the four inputs, so its word is kept.
+__global__ void maxpool2_packed_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long n_out,
+                                       int Ho, int Wo, int C) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out) return;
+  int c = (int)(idx % C);
+  long t = idx / C;
+  int xo = (int)(t % Wo);
+  t /= Wo;
+  int yo = (int)(t % Ho);
+  long img = t / Ho;
+  const long rs = (long)2 * Wo * C;
+  const uint32_t* src = in + ((img * 2 * Ho + 2 * yo) * 2 * Wo + 2 * xo) * (long)C + c;
+  uint32_t w = src[0], w1 = src[C], w2 = src[rs], w3 = src[rs + C];
+  float m = unpack_split(w), f;
+  f = unpack_split(w1); if (f > m) { m = f; w = w1; }
+  f = unpack_split(w2); if (f > m) { m = f; w = w2; }
+  f = unpack_split(w3); if (f > m) { m = f; w = w3; }
+  out[idx] = w;
+}
+
+// global average of every (img, channel) over the hw pixels of a packed NHWC map -> pooled[img][C] fp32
+__global__ void plane_mean_packed_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, long n_img,
+                                         int hw, int C) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * C) return;
+  int c = (int)(idx % C);
+  long img = idx / C;
+  const uint32_t* src = in + img * hw * (long)C + c;
+  float s = 0.f;
+  for (int i = 0; i < hw; i++) s += unpack_split(src[(long)i * C]);
+  out[idx] = s / (float)hw;
 }
 
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
@@ -119,6 +161,49 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
   for (int s = 0; s < 4; s++) pooled[s] = ar.take<float>((size_t)n_img * kSkipC[s]);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
 
+  // Tensor-core trunk: activations live as packed FP16 (hi|lo) NHWC words between layers; the
+  // epilogue of one conv writes exactly what the next conv's operand producers consume.
+  const bool tc_trunk = mm_engine() == 2 || (mm_engine() == 0 && (long)n_img * H * W >= 65536);
+  if (tc_trunk) {
+    const void* cur = crops;
+    int which = 0, h = H, w = W;
+    for (int i = 0; i < 13; i++) {
+      GemmP p = gemm_defaults();
+      p.bias = wts->w[MMMOT_W_VGG_B0 + i];
+      p.M = kVggCout[i];
+      p.K = 9 * kVggCin[i];
+      p.Cin = kVggCin[i];
+      p.H = h; p.W = w;
+      p.S = n_img * h * w;
+      p.X = (const float*)cur;
+      p.Y = buf[which];
+      p.relu = 1;
+      p.tiles_per_group = mm_cdiv(p.S, tc::BN);
+      p.num_tiles = p.tiles_per_group;
+      const uint4* wp = (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i];
+      const float wsc = wts->tc_scale[MMMOT_W_VGG_WP0 + i];
+      const bool timed = mm_timing_on();
+      if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
+      if (i == 0) MM_TRY(gemm_tc_launch<XM_CONV3>(p, wp, wsc, st, 1));     // fp32 NCHW crops in
+      else MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, 1));
+      if (timed) mm_timing_end(st);
+      cur = buf[which]; which ^= 1;
+      if (kPoolAfter[i]) {
+        h /= 2; w /= 2;
+        long n_out = (long)n_img * kVggCout[i] * h * w;
+        maxpool2_packed_kernel<<<mm_cdiv(n_out, 256), 256, 0, st>>>((const uint32_t*)cur, (uint32_t*)buf[which], n_out,
+                                                                   h, w, kVggCout[i]);
+        MM_LAUNCH_CHECK();
+        cur = buf[which]; which ^= 1;
+        int s = kSkipAfter[i];
+        if (s >= 0) {
+          plane_mean_packed_kernel<<<mm_cdiv((long)n_img * kSkipC[s], 128), 128, 0, st>>>(
+              (const uint32_t*)cur, pooled[s], n_img, h * w, kSkipC[s]);
+          MM_LAUNCH_CHECK();
+        }
+      }
+    }
+  } else {
   const float* cur = crops;
   int which = 0, h = H, w = W;
   for (int i = 0; i < 13; i++) {
@@ -134,14 +219,11 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     p.X = cur;
     p.Y = buf[which];
     p.relu = 1;
-    // tensor-core engine for every layer with enough columns to fill the machine
-    const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && p.S >= 4096);
-    p.tiles_per_group = mm_cdiv(p.S, use_tc ? tc::BN : 128);
+    p.tiles_per_group = mm_cdiv(p.S, 128);
     p.num_tiles = p.tiles_per_group;
     const bool timed = mm_timing_on();
     if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
-    if (use_tc) MM_TRY(gemm_tc_launch<XM_CONV3>(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], st));
-    else MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
+    MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
     if (timed) mm_timing_end(st);
     cur = buf[which]; which ^= 1;
     if (kPoolAfter[i]) {
@@ -157,6 +239,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
         MM_LAUNCH_CHECK();
       }
     }
+  }
   }
   for (int s = 0; s < 4; s++) {
     const float* const* q = &wts->w[MMMOT_W_SKIP0 + 10 * s];

@@ -26,6 +26,7 @@
   } while (0)
 
 void mm_count_launch();
+int mm_debug_flags();
 int mm_engine();  // 0 auto, 1 FP32 FFMA engine, 2 tcgen05 engine (mmmot_set_engine)
 bool mm_timing_on();
 void mm_timing_begin(cudaStream_t st, double flop);

@@ -2,20 +2,27 @@
 //
 // Same operand generators and fused epilogue as the FP32 engine in gemm_simt.cuh, but the
 // contraction runs on the 5th-gen tensor cores with FP32-grade accuracy by splitting every FP32
-// operand into two BF16 terms, x = hi + lo (|x - hi - lo| <= 2^-17 |x|), and issuing three BF16
-// MMAs per k-step:  D += Ahi*Bhi + Ahi*Blo + Alo*Bhi   (the dropped lo*lo term is <= 2^-18 relative).
-// Single-pass TF32 / BF16 operands miss the 1e-4 parity bound; this does not.
+// operand into two FP16 terms, x = hi + lo (11 + 11 significant bits: |x - hi - lo| <= 2^-22 |x|),
+// and issuing three FP16 MMAs (FP32 accumulate) per k-step:  D += Ahi*Bhi + Ahi*Blo + Alo*Bhi
+// (the dropped lo*lo term is <= 2^-22 relative).  Weights are pre-scaled by a power of two per
+// matrix so their lo terms stay in FP16's normal range (undone exactly in the epilogue);
+// activations must satisfy |x| < 65504 (conversion saturates).  Single-pass TF32 / BF16 operands
+// miss the 1e-4 parity bound, and a BF16 hi/lo split is ~8x less accurate than this.
 //
 // Persistent, warp-specialised CTA (one per SM), tile 256 (M) x 256 (N), K chunks of 32:
 //   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = output channel), bias / addend /
-//               ReLU, per-thread GroupNorm partial sums (no shuffles), 128-bit stores
+//               ReLU, per-thread GroupNorm partial sums (no shuffles); fp32 [C][S] outputs are
+//               transposed through a per-warp smem scratch so every store is a full 128-byte line;
+//               conv outputs go out as packed FP16 (hi|lo) NHWC words, also 128 bytes per warp
 //   warp  4     MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16), 12 per
 //               chunk; accumulators (2 x 256 fp32 columns) live in TMEM; owns TMEM alloc/dealloc
 //   warp  5     A loader: one thread, cp.async.bulk (TMA engine, no tensor map) of pre-packed
-//               BF16 hi/lo weight tiles, completion on the stage's mbarrier
+//               FP16 hi/lo weight tiles, completion on the stage's mbarrier
 //   warps 6-13  B producers: generate the operand tile (plain load / GroupNorm+ReLU of the
-//               producer layer / pairwise op / 3x3 im2col), split to BF16 hi/lo and write it to
-//               shared memory in the UMMA canonical K-major (no-swizzle) core-matrix layout
+//               producer layer / pairwise op / 3x3 im2col), split to FP16 hi/lo and write it to
+//               shared memory in the UMMA canonical K-major (no-swizzle) core-matrix layout.
+//               XM_CONV3S reads activations already stored as packed FP16 (hi|lo) NHWC words by the
+//               previous conv's epilogue: 128-bit loads, byte-permute de-interleave, no conversion.
 // 3-stage smem ring (64 KB per stage), mbarrier full/empty pipeline, tcgen05.commit releases stages.
 #pragma once
 #include "gemm_simt.cuh"
@@ -32,7 +39,8 @@ constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_HALF;   // 64 KB
 constexpr int A_LBO = 16 * 128, B_LBO = 32 * 128, SBO = 128;
 constexpr int NUM_THREADS = 448;
 constexpr int PRODUCER_T0 = 192;   // first producer thread
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose scratch, one 32x33 fp32 block per warp
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SCRATCH_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt) {
@@ -67,8 +75,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, BF16 inputs, FP32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, FP16 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -84,8 +92,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, M=128, N=256
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=F32 (c_format 1), A=B=F16 (format 0), both K-major, M=128, N=256
+constexpr uint32_t IDESC = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -100,20 +108,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x0 (low half-word) , x1 (high half-word) -> packed bf16x2, round to nearest even
-__device__ __forceinline__ uint32_t pack_bf16x2(float x0, float x1) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
-  return r;
+// (x0, x1) -> hi = packed f16x2 (x0 in the low half-word), lo = packed f16x2 of the residuals
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  float h0, h1;
+  asm("{\n\t.reg .b16 a, b;\n\t"
+      "cvt.rn.satfinite.f16.f32 a, %3;\n\t"
+      "cvt.rn.satfinite.f16.f32 b, %4;\n\t"
+      "mov.b32 %0, {a, b};\n\t"
+      "cvt.f32.f16 %1, a;\n\t"
+      "cvt.f32.f16 %2, b;\n\t}"
+      : "=r"(hi), "=f"(h0), "=f"(h1)
+      : "f"(x0), "f"(x1));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
 struct TcP {
   GemmP g;             // same fields as the FP32 engine (tile width is tc::BN here)
-  const uint4* Wp;     // packed weights: [kchunk][m128 tile][hi|lo][kgroup 4][m8 16][8 rows][8 k] bf16
+  const uint4* Wp;     // packed weights: [kchunk][m128 tile][hi|lo][kgroup 4][m8 16][8 rows][8 k] f16
   int m_tiles;         // ceil(M / 128) (packed rows beyond M are zero)
   int k_chunks;        // ceil(K / 32)
   int mt_per_cta;      // 1 or 2 (128-row subtiles per CTA tile)
+  float out_scale;     // 2^-s: undoes the power-of-two pre-scaling of the packed weights
+  int out_packed;      // 1: Y is uint32 NHWC [column][M] of packed FP16 (hi | lo << 16) words
+  int dbg;             // profiling experiments only (mmmot_set_debug): 1 skip epilogue work, 2 skip A loads,
+                       // 4 skip B generation, 8 skip MMA issue
 };
+
+// fp32 -> packed (hi | lo << 16) FP16 pair with x ~= hi + lo
+__device__ __forceinline__ uint32_t pack_split_f16(float x) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 a, b;\n\t.reg .f32 f;\n\t"
+      "cvt.rn.satfinite.f16.f32 a, %1;\n\t"
+      "cvt.f32.f16 f, a;\n\t"
+      "sub.f32 f, %1, f;\n\t"
+      "cvt.rn.satfinite.f16.f32 b, f;\n\t"
+      "mov.b32 %0, {a, b};\n\t}"
+      : "=r"(r)
+      : "f"(x));
+  return r;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
@@ -128,6 +161,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES), tempty_bar = bar0 + 8u * (2 * STAGES + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
+  float* scratch = reinterpret_cast<float*>(sm + STAGES * STAGE_BYTES + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = P.mt_per_cta;
@@ -158,7 +192,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
   if (warp < 4) {
     // =============================== EPILOGUE ===============================
     uint32_t tphase = 0;
-    const int hw = (MODE == XM_CONV3) ? p.H * p.W : 1;
+    float* sc = scratch + warp * (32 * 33);
+    uint32_t* ypk = reinterpret_cast<uint32_t*>(p.Y);
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mg = (int)(t % mgroups);
       const int nt = (int)(t / mgroups);
@@ -169,60 +204,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       tphase ^= 1;
       tc_fence_after();
       for (int mt = 0; mt < MT; mt++) {
-        const int co = (mg * MT + mt) * 128 + warp * 32 + lane;
+        const int co_base = (mg * MT + mt) * 128 + warp * 32;
+        const int co = co_base + lane;
         const bool rowok = co < p.M;
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
         double d1 = 0.0, d2 = 0.0;
-        float* rowp = nullptr;
-        if (MODE != XM_CONV3 && p.Y && rowok) rowp = p.Y + (long)g * p.y_gs + (long)co * p.y_ms + c0;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; cc++) {
           if (cc * 32 >= len) break;   // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 256 + cc * 32), v);
-          if (!rowok) continue;
+          if (P.dbg & 1) continue;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            float x = __uint_as_float(v[j]) + bv;
+            float x = fmaf(__uint_as_float(v[j]), P.out_scale, bv);
             const int col = cc * 32 + j;
-            if (p.addend && col < len) x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
+            if (p.addend && rowok && col < len)
+              x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
             if (p.relu) x = fmaxf(x, 0.f);
             v[j] = __float_as_uint(x);
             if (col < len) { s1 += x; s2 += x * x; }
           }
           d1 += (double)s1; d2 += (double)s2;
-          if (p.Y) {
+          if (!p.Y) continue;
+          if (P.out_packed) {
+            // NHWC packed FP16 (hi|lo): word [column][channel]; a warp writes 32 consecutive channels
+            if (rowok) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const int col = cc * 32 + q * 4;
-              if (col >= len) break;
-              float* dst;
-              bool vec;
-              if (MODE == XM_CONV3) {
-                const int s = c0 + col;
-                const int img = s / hw, pix = s - img * hw;
-                dst = p.Y + ((long)img * p.M + co) * hw + pix;
-                vec = ((hw & 3) == 0) && (col + 3 < len);
-              } else {
-                dst = rowp + col;
-                vec = (col + 3 < len) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-              }
-              if (vec) {
-                *reinterpret_cast<uint4*>(dst) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              } else {
-                for (int e = 0; e < 4; e++) {
-                  if (col + e >= len) break;
-                  if (MODE == XM_CONV3) {
-                    const int s = c0 + col + e;
-                    const int img = s / hw, pix = s - img * hw;
-                    p.Y[((long)img * p.M + co) * hw + pix] = __uint_as_float(v[q * 4 + e]);
-                  } else {
-                    dst[e] = __uint_as_float(v[q * 4 + e]);
-                  }
-                }
+              for (int j = 0; j < 32; j++) {
+                const int col = cc * 32 + j;
+                if (col < len) ypk[(long)(c0 + col) * p.M + co] = pack_split_f16(__uint_as_float(v[j]));
               }
             }
+          } else {
+            // fp32 [C][S]: transpose the 32x32 block through smem so each store is one 128-byte line
+#pragma unroll
+            for (int j = 0; j < 32; j++) sc[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int col = cc * 32 + lane;
+            if (col < len) {
+              float* dst = p.Y + (long)g * p.y_gs + (long)co_base * p.y_ms + c0 + col;
+              const int rmax = min(32, p.M - co_base);
+#pragma unroll 8
+              for (int r = 0; r < rmax; r++) dst[(long)r * p.y_ms] = sc[r * 33 + lane];
+            }
+            __syncwarp();
           }
         }
         if (p.part && rowok) p.part[(long)nt * p.M + co] = make_double2(d1, d2);
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
           const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_SUB;
 #pragma unroll
           for (int mt = 0; mt < 2; mt++) {
-            if (mt < MT) {
+            if (mt < MT && !(P.dbg & 8)) {
 #pragma unroll
               for (int ks = 0; ks < 2; ks++) {
                 const uint64_t a_hi = smem_desc(sa + mt * A_SUB + ks * 2 * A_LBO, A_LBO, SBO);
@@ -253,9 +280,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
                 const uint64_t b_hi = smem_desc(sb + ks * 2 * B_LBO, B_LBO, SBO);
                 const uint64_t b_lo = smem_desc(sb + B_HALF + ks * 2 * B_LBO, B_LBO, SBO);
                 const uint32_t d = tmem_base + (uint32_t)(mt * 256);
-                umma_bf16(d, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
-                umma_bf16(d, a_hi, b_lo, IDESC, 1u);
-                umma_bf16(d, a_lo, b_hi, IDESC, 1u);
+                umma_f16(d, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
+                umma_f16(d, a_hi, b_lo, IDESC, 1u);
+                umma_f16(d, a_lo, b_hi, IDESC, 1u);
               }
             }
           }
@@ -277,6 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
           const int s = it % STAGES;
           mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
           const uint32_t bytes = (uint32_t)nmt * A_SUB;
+          if (P.dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_expect_tx(full_bar(s), bytes);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(P.Wp) + ((size_t)kc * P.m_tiles + mt0) * A_SUB;
           bulk_g2s(base + s * STAGE_BYTES, src, bytes, full_bar(s));
@@ -286,41 +314,139 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
     __syncwarp();
   } else {
     // =============================== B PRODUCERS ===============================
-    const int col = tid - PRODUCER_T0;  // 0..255: this thread's column of the tile
-    uint32_t it = 0;
-    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    // The gather of chunk i+1 (global loads into registers) is issued before chunk i is converted and
+    // published, so load latency overlaps the conversion work.
+    const int pt = tid - PRODUCER_T0;  // 0..255
+    const long my_tiles = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long my_chunks = my_tiles * KC;
+    long gi = 0;  // next chunk to gather
+
+    auto tile_cols = [&](long chunk, int& g, int& c0, int& len) {
+      const long t = blockIdx.x + (chunk / KC) * gridDim.x;
       const int nt = (int)(t / mgroups);
-      int g, c0, len;
       if (p.tile_tab) { int4 tt = p.tile_tab[nt]; g = tt.x; c0 = tt.y; len = tt.z; }
       else { g = nt / p.tiles_per_group; c0 = (nt - g * p.tiles_per_group) * BN; len = min(BN, p.S - c0); }
-      const bool colok = col < len;
-      long coff = 0;
-      int aux = 0, pi = 0;
-      if (MODE == XM_DIRECT || MODE == XM_NORM_RELU) {
-        coff = (long)g * p.x_gs + c0 + col;
-      } else if (MODE == XM_CONV3) {
-        const int s = c0 + col, hw = p.H * p.W;
-        const int img = s / hw, pix = s - img * hw;
-        const int y = pix / p.W, x = pix - y * p.W;
-        coff = (long)img * p.Cin * hw + pix;
-#pragma unroll
-        for (int tp = 0; tp < 9; tp++) {
-          const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) aux |= 1 << tp;
-        }
-        if (!colok) aux = 0;
-      } else {
-        const int s = c0 + col;
-        pi = s / p.m;
-        aux = p.n + (s - pi * p.m);
-      }
-      const uint32_t row_off = (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;
+    };
+    auto arrive_full = [&](int s) {
+      fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+    };
 
-      for (int kc = 0; kc < KC; kc++, it++) {
-        const int s = it % STAGES;
+    if (MODE == XM_CONV3S) {
+      // ---- packed-FP16 NHWC activations: item = (pixel, k-group of 8 channels) = 32 contiguous bytes ----
+      const uint32_t* X = reinterpret_cast<const uint32_t*>(p.X);
+      const int kg = pt & 3;
+      long pbase[4];   // word offset of (img, y, x, channel 0) for this thread's 4 pixels
+      int pmask[4];    // 9-bit tap validity
+      auto gather = [&](uint4 (&w)[8]) {
+        if (gi >= my_chunks) { gi++; return; }
+        const int kc = (int)(gi % KC);
+        if (kc == 0) {
+          int g, c0, len;
+          tile_cols(gi, g, c0, len);
+          const int hw = p.H * p.W;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int pl = (pt >> 2) + 64 * i;
+            const int s = c0 + pl;
+            const int img = s / hw, pix = s - img * hw;
+            const int y = pix / p.W, x = pix - y * p.W;
+            pbase[i] = (long)s * p.Cin;
+            int mk = 0;
+#pragma unroll
+            for (int tp = 0; tp < 9; tp++) {
+              const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) mk |= 1 << tp;
+            }
+            pmask[i] = pl < len ? mk : 0;
+          }
+        }
+        gi++;
+        if (P.dbg & 4) return;
         const int k0 = kc * BK;
-        float v[BK];
-        // ---- gather (global loads issued before waiting for the smem slot) ----
+        const int tap = k0 / p.Cin, ci0 = k0 - tap * p.Cin;     // K order: k = tap*Cin + ci, Cin % 32 == 0
+        const long d = (long)((tap / 3 - 1) * p.W + (tap % 3 - 1)) * p.Cin + ci0 + kg * 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if ((pmask[i] >> tap) & 1) {
+            const uint4* src = reinterpret_cast<const uint4*>(X + pbase[i] + d);
+            w[2 * i] = __ldg(src);
+            w[2 * i + 1] = __ldg(src + 1);
+          } else {
+            w[2 * i] = make_uint4(0, 0, 0, 0);
+            w[2 * i + 1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      };
+      auto publish = [&](long it, const uint4 (&w)[8]) {
+        const int s = (int)(it % STAGES);
+        mbar_wait(empty_bar(s), (uint32_t)((it / STAGES) & 1) ^ 1u);
+        uint8_t* bh = sm + s * STAGE_BYTES + 2 * A_SUB + kg * B_LBO;
+        if (!(P.dbg & 4)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int pl = (pt >> 2) + 64 * i;
+            const uint32_t off = (uint32_t)(pl >> 3) * 128u + (uint32_t)(pl & 7) * 16u;
+            const uint4 a = w[2 * i], b = w[2 * i + 1];
+            // word = hi | lo << 16  ->  separate hi / lo streams
+            *reinterpret_cast<uint4*>(bh + off) =
+                make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410),
+                           __byte_perm(b.x, b.y, 0x5410), __byte_perm(b.z, b.w, 0x5410));
+            *reinterpret_cast<uint4*>(bh + B_HALF + off) =
+                make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632),
+                           __byte_perm(b.x, b.y, 0x7632), __byte_perm(b.z, b.w, 0x7632));
+          }
+        }
+        arrive_full(s);
+      };
+      uint4 wa[8], wb[8];
+      gather(wa);
+      for (long it = 0; it < my_chunks; it += 2) {
+        gather(wb);
+        publish(it, wa);
+        if (it + 1 < my_chunks) {
+          gather(wa);
+          publish(it + 1, wb);
+        }
+      }
+    } else {
+      // ---- fp32 sources: one thread per tile column, 32 k per chunk ----
+      const int col = pt;
+      const uint32_t row_off = (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;
+      int g = 0, aux = 0, pi = 0;
+      bool colok = false;
+      long coff = 0;
+      auto gather = [&](float (&v)[BK]) {
+        if (gi >= my_chunks) { gi++; return; }
+        const int kc = (int)(gi % KC);
+        if (kc == 0) {
+          int c0, len;
+          tile_cols(gi, g, c0, len);
+          colok = col < len;
+          aux = 0;
+          if (MODE == XM_DIRECT || MODE == XM_NORM_RELU) {
+            coff = (long)g * p.x_gs + c0 + col;
+          } else if (MODE == XM_CONV3) {
+            const int s = c0 + col, hw = p.H * p.W;
+            const int img = s / hw, pix = s - img * hw;
+            const int y = pix / p.W, x = pix - y * p.W;
+            coff = (long)img * p.Cin * hw + pix;
+#pragma unroll
+            for (int tp = 0; tp < 9; tp++) {
+              const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) aux |= 1 << tp;
+            }
+            if (!colok) aux = 0;
+          } else {
+            const int s = c0 + col;
+            pi = s / p.m;
+            aux = p.n + (s - pi * p.m);
+          }
+        }
+        gi++;
+        if (P.dbg & 4) return;
+        const int k0 = kc * BK;
         if (MODE == XM_DIRECT || MODE == XM_NORM_RELU) {
 #pragma unroll
           for (int e = 0; e < BK; e++) {
@@ -334,7 +460,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
             v[e] = x;
           }
         } else if (MODE == XM_CONV3) {
-          // K order: k = ci*9 + tap (the 9 taps of one input plane are adjacent -> L1 reuse)
+          // fp32 NCHW input (first VGG layer); K order: k = ci*9 + tap
           int ci = k0 / 9, tap = k0 - ci * 9;
           const int hw = p.H * p.W;
 #pragma unroll
@@ -362,26 +488,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
             v[e] = x;
           }
         }
-        // ---- split to bf16 hi / lo and publish in the canonical layout ----
-        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+      };
+      // split to f16 hi / lo and publish chunk `it` in the canonical layout
+      auto publish = [&](long it, const float (&v)[BK]) {
+        const int s = (int)(it % STAGES);
+        mbar_wait(empty_bar(s), (uint32_t)((it / STAGES) & 1) ^ 1u);
         uint8_t* bh = sm + s * STAGE_BYTES + 2 * A_SUB;
+        if (!(P.dbg & 4)) {
 #pragma unroll
-        for (int kg = 0; kg < BK / 8; kg++) {
-          uint32_t h[4], l[4];
+          for (int kg = 0; kg < BK / 8; kg++) {
+            uint32_t h[4], l[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const float x0 = v[kg * 8 + 2 * q], x1 = v[kg * 8 + 2 * q + 1];
-            const uint32_t hh = pack_bf16x2(x0, x1);
-            const float r0 = x0 - __uint_as_float(hh << 16), r1 = x1 - __uint_as_float(hh & 0xffff0000u);
-            h[q] = hh;
-            l[q] = pack_bf16x2(r0, r1);
+            for (int q = 0; q < 4; q++) split_f16x2(v[kg * 8 + 2 * q], v[kg * 8 + 2 * q + 1], h[q], l[q]);
+            *reinterpret_cast<uint4*>(bh + kg * B_LBO + row_off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(bh + B_HALF + kg * B_LBO + row_off) = make_uint4(l[0], l[1], l[2], l[3]);
           }
-          *reinterpret_cast<uint4*>(bh + kg * B_LBO + row_off) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(bh + B_HALF + kg * B_LBO + row_off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(s));
+        arrive_full(s);
+      };
+      float va[BK], vb[BK];
+      gather(va);
+      for (long it = 0; it < my_chunks; it += 2) {
+        gather(vb);
+        publish(it, va);
+        if (it + 1 < my_chunks) {
+          gather(va);
+          publish(it + 1, vb);
+        }
       }
     }
   }
@@ -396,9 +529,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
 
 }  // namespace tc
 
-// Host launcher.  `Wp` = weights packed by mmmot_b200/weights.py::pack_tc.
+// Host launcher.  `Wp` = weights packed by mmmot_b200/weights.py::pack_tc; out_scale = 2^-s of that packing.
+// out_packed: write Y as packed FP16 (hi|lo) NHWC words (conv layers) instead of fp32 [C][S].
 template <int MODE>
-static int gemm_tc_launch(const GemmP& g, const uint4* Wp, cudaStream_t st) {
+static int gemm_tc_launch(const GemmP& g, const uint4* Wp, float out_scale, cudaStream_t st, int out_packed = 0) {
   if (!Wp || g.num_tiles <= 0) return MMMOT_E_ARG;
   static int sms = 0;
   if (!sms) {
@@ -418,6 +552,9 @@ static int gemm_tc_launch(const GemmP& g, const uint4* Wp, cudaStream_t st) {
   P.m_tiles = (g.M + 127) / 128;
   P.k_chunks = (g.K + tc::BK - 1) / tc::BK;
   P.mt_per_cta = P.m_tiles >= 2 ? 2 : 1;
+  P.out_scale = out_scale;
+  P.out_packed = out_packed;
+  P.dbg = mm_debug_flags();
   const long mgroups = (P.m_tiles + P.mt_per_cta - 1) / P.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);

@@ -157,13 +157,14 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.Y = dst[i]; p.y_ms = P;
     p.part = w.part;
     const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
+    const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
     if (i == 0) {
-      if (use_tc) MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, st));
+      if (use_tc) MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st));
       else MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
     } else {
       p.sc = (i == 1) ? w.sc1 : w.sc;
       p.sh = (i == 1) ? w.sh1 : w.sh;
-      if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, wp, st));
+      if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, wp, wps, st));
       else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     }
     MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st));
@@ -192,7 +193,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.Y = w.big; p.y_ms = P;
     p.part = w.part;
     p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
-    if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], st));
+    if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], st));
     else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,

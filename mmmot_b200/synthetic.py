@@ -47,6 +47,21 @@ def synthetic_state_dict(fusion="C", seed=0):
     return sd
 
 
+def structured_crops(noise, gen):
+    """Image crops are mean/std-normalised pixels (reference utils/build_util.py:111-112), i.e.
+    ~N(0,1) per pixel, but different detections show different objects.  Pure white noise makes
+    every crop's pooled VGG feature nearly identical, so the fusion GroupNorm (per channel over the
+    L detections) divides by a ~zero spread and amplifies fp32 round-off ~20-100x for ANY
+    implementation.  Give each detection its own contrast, brightness and low-frequency content,
+    like real crops have (|mean|/std of the pre-norm fusion channels drops from ~18 to ~4)."""
+    L, hw = noise.shape[0], noise.shape[-1]
+    lf = torch.nn.functional.interpolate(torch.randn(L, 3, 4, 4, generator=gen), size=hw, mode="bilinear",
+                                         align_corners=False)
+    contrast = torch.rand(L, 1, 1, 1, generator=gen) + 0.25
+    bright = torch.randn(L, 3, 1, 1, generator=gen) * 0.5
+    return noise * contrast + 1.5 * lf + bright
+
+
 def synthetic_pair(n, m=None, pts=128, hw=64, seed=0, ragged=False):
     """One frame-pair in the exact layout ``TestSequence.__getitem__`` + the DataLoader hand to
     ``TrackingNet.forward`` (reference: dataset/test_seq_dataset.py:227-246, eval_seq.py:144-153):
@@ -57,7 +72,7 @@ def synthetic_pair(n, m=None, pts=128, hw=64, seed=0, ragged=False):
     m = n if m is None else m
     L = n + m
     g = torch.Generator().manual_seed(1234 + seed)
-    dets = torch.randn(L, 3, hw, hw, generator=g)
+    dets = structured_crops(torch.randn(L, 3, hw, hw, generator=g), g)
     if ragged:
         cnt = torch.randint(1, 2 * pts, (L,), generator=g)
     else:

@@ -44,23 +44,30 @@ def _fold_bn(sd, conv, bn):
 
 
 def pack_tc(wt):
-    """Wt[K][M] (fp32/fp64) -> uint8 tensor holding the tcgen05 operand tiles of W = Wt^T:
-    [k chunk 32][m tile 128][hi|lo][k group 4][m group 16][8 rows][8 k] bf16, zero padded.
-    hi = bf16(w) (round-to-nearest-even), lo = bf16(w - hi): w = hi + lo to 2^-17 relative."""
-    w = wt.t().float().contiguous()                       # [M][K]
+    """Wt[K][M] (fp32/fp64) -> (uint8 tensor, out_scale): the tcgen05 operand tiles of W = Wt^T,
+    [k chunk 32][m tile 128][hi|lo][k group 4][m group 16][8 rows][8 k] fp16, zero padded.
+    W is pre-scaled by 2^s (max |W 2^s| <= 2048) so that lo = fp16(w - hi) stays in fp16's normal
+    range; hi = fp16(w) (round-to-nearest-even): w = hi + lo to 2^-22 relative.  out_scale = 2^-s
+    is applied to the fp32 accumulators in the epilogue (exact)."""
+    import math
+    w = wt.t().double().contiguous()                      # [M][K]
     M, K = w.shape
+    amax = float(w.abs().max())
+    sexp = int(math.floor(math.log2(2048.0 / amax))) if amax > 0 else 0
+    w = (w * (2.0 ** sexp)).float()
     mt, kc = (M + 127) // 128, (K + 31) // 32
     pad = torch.zeros(mt * 128, kc * 32, dtype=torch.float32)
     pad[:M, :K] = w
-    hi = pad.to(torch.bfloat16)
-    lo = (pad - hi.float()).to(torch.bfloat16)
+    hi = pad.to(torch.float16)
+    lo = (pad - hi.float()).to(torch.float16)
     both = torch.stack([hi, lo], 0).view(2, mt, 16, 8, kc, 4, 8)      # hl, mt, mg, r, kc, kg, e
     both = both.permute(4, 1, 0, 5, 2, 3, 6).contiguous()              # kc, mt, hl, kg, mg, r, e
-    return both.view(torch.int16).reshape(-1).view(torch.uint8)
+    return both.view(torch.int16).reshape(-1).view(torch.uint8), 2.0 ** (-sexp)
 
 
 def prepare(state_dict, fusion):
-    """-> (list of fp32 CPU tensors indexed by weight id (None = unused), trans1 3x3, trans2 64x64)."""
+    """-> (list of fp32 CPU tensors indexed by weight id (None = unused), trans1 3x3, trans2 64x64,
+    per-id tensor-core output scales)."""
     sd = {k: v.detach().cpu() for k, v in state_dict.items()}
     out = [None] * W["COUNT"]
     f64 = lambda k: sd[k].double()
@@ -149,20 +156,27 @@ def prepare(state_dict, fusion):
 
     out = [None if t is None else t.contiguous().float() for t in out]
     # tensor-core operand tiles (bytes, viewed as float32 words for the flat buffer)
+    scales = [0.0] * W["COUNT"]
+
+    def put(wid, wt):
+        out[wid], scales[wid] = pack_tc(wt)
     i = 0
     for s_, stage in enumerate(VGG_STAGES):
         for idx, cin, cout in stage:
             w, _ = _fold_bn(sd, f"appearance.layers.{s_}.{idx}", f"appearance.layers.{s_}.{idx + 1}")
-            out[W["VGG_WP0"] + i] = pack_tc(w.reshape(cout, cin * 9).t())        # K order ci*9 + tap
+            if i == 0:
+                put(W["VGG_WP0"] + i, w.reshape(cout, cin * 9).t())    # fp32 NCHW input: K order ci*9 + tap
+            else:
+                put(W["VGG_WP0"] + i, out[W["VGG_WT0"] + i])          # packed NHWC input: K order tap*Cin + ci
             i += 1
-    for j in range(1, 5):
-        out[W["PN_WP1"] + j] = pack_tc(out[W["PN_L1"] + 4 * j])
-    out[W["PN_WHAP"]] = pack_tc(out[W["PN_WHAT"]])
-    out[W["AF_W01P"]] = pack_tc(out[W["AF_W01T"]])
-    out[W["AF_W2P"]] = pack_tc(out[W["AF_W2T"]])
-    out[W["AF_W3P"]] = pack_tc(out[W["AF_W3T"]])
+    for j in range(5):
+        put(W["PN_WP1"] + j, out[W["PN_L1"] + 4 * j])
+    put(W["PN_WHAP"], out[W["PN_WHAT"]])
+    put(W["AF_W01P"], out[W["AF_W01T"]])
+    put(W["AF_W2P"], out[W["AF_W2T"]])
+    put(W["AF_W3P"], out[W["AF_W3T"]])
     out = [t.view(torch.float32) if (t is not None and t.dtype == torch.uint8) else t for t in out]
-    return out, t1.float(), t2.float()
+    return out, t1.float(), t2.float(), scales
 
 
 class DeviceWeights:
@@ -170,7 +184,7 @@ class DeviceWeights:
     handed to the C ABI."""
 
     def __init__(self, state_dict, fusion, device):
-        tensors, self.trans1, self.trans2 = prepare(state_dict, fusion)
+        tensors, self.trans1, self.trans2, scales = prepare(state_dict, fusion)
         offs, total = [], 0
         for t in tensors:
             offs.append(total)
@@ -185,6 +199,7 @@ class DeviceWeights:
         base = self.flat.data_ptr()
         for i, (t, o) in enumerate(zip(tensors, offs)):
             self.table.w[i] = None if t is None else base + 4 * o
+            self.table.tc_scale[i] = scales[i]
         self.ptr = ctypes.pointer(self.table)
         self.trans1 = self.trans1.to(device)
         self.trans2 = self.trans2.to(device)

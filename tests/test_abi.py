@@ -64,7 +64,7 @@ def test_state_dict_schema(fusion, nkeys, numel):
 
 def test_prepare_folds_bn_and_stn():
     sd = synthetic_state_dict("C", seed=2)
-    w, t1, t2 = prepare(sd, "C")
+    w, t1, t2, scales = prepare(sd, "C")
     assert sum(t is not None for t in w) == _lib.W["COUNT"]
     # BN fold of the first VGG conv: y = conv(x)*s + shift, checked on a random input
     x = torch.randn(2, 3, 8, 8)

@@ -41,10 +41,12 @@ def test_tcgen05_contraction_vs_fp64(M, K, S):
     Wt, X, b = torch.randn(K, M, generator=g), torch.randn(K, S, generator=g), torch.randn(M, generator=g)
     ref = Wt.double().t() @ X.double() + b.double()[:, None]
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    Wt_d, X_d, b_d, Wp = Wt.cuda(), X.cuda(), b.cuda(), pack_tc(Wt).cuda()
+    Wt_d, X_d, b_d = Wt.cuda(), X.cuda(), b.cuda()
+    Wp, wps = pack_tc(Wt)
+    Wp = Wp.cuda()
     for eng in (1, 2):
         Y = torch.full((M, S), float("nan"), device="cuda")
-        assert lib.mmmot_debug_linear(vp(Wt_d), vp(Wp), vp(b_d), vp(X_d), vp(Y), M, K, S, eng, None) == 0
+        assert lib.mmmot_debug_linear(vp(Wt_d), vp(Wp), wps, vp(b_d), vp(X_d), vp(Y), M, K, S, eng, None) == 0
         assert relerr(Y, ref) < 3e-5, eng
 
 

@@ -51,8 +51,11 @@ def stage(fusion, op, sm, n, m, pts, hw, ragged, seed):
 
 try:
     P(torch.cuda.get_device_name(0))
+    ENG = os.environ.get("MMMOT_DIAG_ENGINE", "auto")
+    mmmot_b200.set_engine(ENG)
+    P("engine:", ENG)
     for cfg in (("A", "multiply", "none", 8, 8, 32, 32, False, 1), ("C", "minus_abs", "dual_add", 6, 9, 24, 64, True, 2),
-                ("B", "multiply", "single", 16, 16, 64, 64, True, 3)):
+                ("B", "multiply", "single", 16, 16, 64, 64, True, 3), ("C", "minus_abs", "dual_add", 32, 32, 128, 64, True, 4)):
         try:
             stage(*cfg)
         except Exception:
