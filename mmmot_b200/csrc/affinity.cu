@@ -6,8 +6,8 @@
 // 100.7 MB per pair at N=M=128) is generated inside the first contraction's operand loader and
 // never exists in HBM; affinity conv1.0 and new/end conv0 (both 512->512 on the same x) run as
 // ONE 512->1024 contraction.
-#include "gemm_tc.cuh"
 #include "norm_ops.cuh"
+#include "tc_ops.cuh"
 
 namespace {
 
@@ -46,6 +46,60 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
     for (int w2 = 0; w2 < nw; w2++) t += colacc[w2 * M + j];
     vout[j] = t / (float)N;
   }
+}
+
+// ---- channels-last (tensor-core path) variants: y[(g*N + i)*M + j][ld] ----
+// end_vec[c][i] = mean_j relu(GN(y0))   -> V[c][g*(M+N) + M + i];  one CTA per (g, i), threads over channels
+__global__ void end_mean_cl_kernel(const float* __restrict__ y, long ld, int coff, const float* __restrict__ sc,
+                                   const float* __restrict__ sh, int N, int M, long ldv, float* __restrict__ V) {
+  const int g = blockIdx.x / N, i = blockIdx.x % N;
+  const float* src = y + ((long)(g * N + i) * M) * ld + coff;
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+    const float a = sc[g * 512 + c], b = sh[g * 512 + c];
+    float acc = 0.f;
+    for (int j = 0; j < M; j++) acc += fmaxf(fmaf(src[(long)j * ld + c], a, b), 0.f);
+    V[(long)c * ldv + (long)g * (M + N) + M + i] = acc / (float)M;
+  }
+}
+// new_vec[c][j] = mean_i relu(GN(y0))   -> V[c][g*(M+N) + j];  one CTA per (g, j)
+__global__ void new_mean_cl_kernel(const float* __restrict__ y, long ld, int coff, const float* __restrict__ sc,
+                                   const float* __restrict__ sh, int N, int M, long ldv, float* __restrict__ V) {
+  const int g = blockIdx.x / M, j = blockIdx.x % M;
+  const float* src = y + ((long)g * N * M + j) * ld + coff;
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+    const float a = sc[g * 512 + c], b = sh[g * 512 + c];
+    float acc = 0.f;
+    for (int i = 0; i < N; i++) acc += fmaxf(fmaf(src[(long)i * M * ld + c], a, b), 0.f);
+    V[(long)c * ldv + (long)g * (M + N) + j] = acc / (float)N;
+  }
+}
+// z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : 8 lanes per row (4 float4 each), fixed-order shuffle tree
+__global__ void link_logit_cl_kernel(const float* __restrict__ y3, const float* __restrict__ sc,
+                                     const float* __restrict__ sh, const float* __restrict__ w4,
+                                     const float* __restrict__ b4, long rows, int NM, float* __restrict__ z) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long row = t >> 3;
+  const int sub = (int)(t & 7);
+  float acc = 0.f;
+  if (row < rows) {
+    const int g = (int)(row / NM);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = (sub * 4 + q) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(y3 + row * 128 + c);
+      const float4 a = *reinterpret_cast<const float4*>(sc + g * 128 + c);
+      const float4 b = *reinterpret_cast<const float4*>(sh + g * 128 + c);
+      const float4 w = *reinterpret_cast<const float4*>(w4 + c);
+      acc = fmaf(w.x, fmaxf(fmaf(x.x, a.x, b.x), 0.f), acc);
+      acc = fmaf(w.y, fmaxf(fmaf(x.y, a.y, b.y), 0.f), acc);
+      acc = fmaf(w.z, fmaxf(fmaf(x.z, a.z, b.z), 0.f), acc);
+      acc = fmaf(w.w, fmaxf(fmaf(x.w, a.w, b.w), 0.f), acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (row < rows && sub == 0) z[row] = acc + b4[0];
 }
 
 // Tile table for the new/end MLP: group 2g = new columns (len M), 2g+1 = end columns (len N).
@@ -143,6 +197,7 @@ __global__ void softmax_apply_kernel(const float* __restrict__ z, int mode, int 
 
 struct AfWs {
   float *y01, *y2, *y3, *z;
+  uint32_t* xp;   // tensor-core path: packed FP16 (hi|lo) normalised activations [G*NM][512]
   float *sc1, *sh1, *sc0, *sh0, *sc2, *sh2, *sc3, *sh3;
   float *v, *h1, *h2, *nsc1, *nsh1, *nsc2, *nsh2;
   float *rmax, *rsum, *cmax, *csum;
@@ -158,6 +213,7 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.y2 = a.take<float>(G * 512 * NM);
   w.y3 = a.take<float>(G * 128 * NM);
   w.z = a.take<float>(G * NM);
+  w.xp = a.take<uint32_t>(G * NM * 512);
   w.sc1 = a.take<float>(G * 512); w.sh1 = a.take<float>(G * 512);
   w.sc0 = a.take<float>(G * 512); w.sh0 = a.take<float>(G * 512);
   w.sc2 = a.take<float>(G * 512); w.sh2 = a.take<float>(G * 512);
@@ -172,14 +228,14 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.tiles = a.take<int4>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)));
   w.cnt = a.take<int>(2 * G);
   w.gstart = a.take<int>(2 * G + 1);
-  w.part = a.take<double2>(G * mm_cdiv(NM, 128) * 1024);
+  w.part = a.take<double2>(G * 2 * mm_cdiv(NM, 256) * 1024);   // covers 1 partial per 128-tile and 2 per 256-tile
   w.npart = a.take<double2>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);
   return w;
 }
 
 template <int MODE>
-int run_layer(GemmP& p, const mmmot_weights* wts, int wid, bool use_tc, cudaStream_t st) {
-  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wts->w[wid], wts->tc_scale[wid], st) : gemm_simt_launch<MODE>(p, st);
+int run_layer(GemmP& p, const mmmot_weights* wts, int wid, bool use_tc, int out_mode, cudaStream_t st) {
+  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wts->w[wid], wts->tc_scale[wid], st, out_mode) : gemm_simt_launch<MODE>(p, st);
 }
 
 }  // namespace
@@ -206,30 +262,41 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   const int tpg = mm_cdiv(NM, use_tc ? tc::BN : 128);
   const float* const* W = wts->w;
 
-  // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor
+  // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor.
+  // FP32 engine: y01[g][1024][NM].  Tensor-core engine: channels-last y01[g*NM + s][1024].
+  const int pm = use_tc ? 2 : 1;   // GroupNorm partials per column tile
   {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.X = feats; p.n = n; p.m = m; p.Lf = L;
-    p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
+    p.Y = w.y01;
+    if (use_tc) { p.y_gs = NM; p.y_ms = 1024; } else { p.y_gs = 1024L * NM; p.y_ms = NM; }
     p.part = w.part;
-    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wts, MMMOT_W_AF_W01P, use_tc, st)
-            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wts, MMMOT_W_AF_W01P, use_tc, st)
-                                                 : run_layer<XM_PAIR_SUB>(p, wts, MMMOT_W_AF_W01P, use_tc, st);
+    const int om = tc::OUT_CL;
+    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st)
+                                                 : run_layer<XM_PAIR_SUB>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st);
     if (r) return r;
   }
   // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),
   // 512..1023 = conv0 -> GroupNorm(1,512) (one group over 512 x N x M; new_end.py:50)
-  MM_TRY(stats_reduce(w.part, 1024, G, tpg, nullptr, w.stats, st));
+  MM_TRY(stats_reduce(w.part, 1024, G, tpg, nullptr, w.stats, st, pm));
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G1W], W[MMMOT_W_AF_G1B], nullptr, NM, G, 512, 1, w.sc1, w.sh1, st, 1024, 0));
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G0W], W[MMMOT_W_AF_G0B], nullptr, NM, G, 512, 512, w.sc0, w.sh0, st, 1024, 512));
 
   // ---- new / end indicator on y0 = rows 512..1023 of y01 ----
   const long ldv = (long)G * (n + m);
-  rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
-                                                             n, m, ldv, w.v);
-  MM_LAUNCH_CHECK();
+  if (use_tc) {
+    end_mean_cl_kernel<<<G * n, 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
+    MM_LAUNCH_CHECK();
+    new_mean_cl_kernel<<<G * m, 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
+    MM_LAUNCH_CHECK();
+  } else {
+    rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
+                                                               n, m, ldv, w.v);
+    MM_LAUNCH_CHECK();
+  }
   const int tn = mm_cdiv(n, 128), tm_ = mm_cdiv(m, 128), ne_tiles = G * (tn + tm_);
   ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G + 1), 128), 128, 0, st>>>(G, n, m, tn, tm_, w.tiles, w.cnt, w.gstart);
   MM_LAUNCH_CHECK();
@@ -254,27 +321,51 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     MM_LAUNCH_CHECK();
   }
 
-  // ---- affinity MLP layers 2, 3 on y1 = rows 0..511 of y01 ----
-  {
+  // ---- affinity MLP layers 2, 3 on y1 = channels 0..511 of y01 ----
+  if (use_tc) {
+    // GroupNorm+ReLU applied once per element by norm_split -> packed FP16 operand of the next contraction
+    const long rows = (long)G * NM;
+    MM_TRY(norm_split(w.y01, 1024, w.sc1, w.sh1, 512, rows, NM, nullptr, 0, w.xp, 512, st));
+    GemmP p = gemm_defaults();
+    p.bias = W[MMMOT_W_AF_B2]; p.M = 512; p.K = 512;
+    p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
+    p.X = (const float*)w.xp; p.Cin = 512; p.x_gs = NM;
+    p.Y = w.y2; p.y_gs = NM; p.y_ms = 512;
+    p.part = w.part;
+    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W2P], wts->tc_scale[MMMOT_W_AF_W2P], st, tc::OUT_CL));
+    MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st, 2));
+    MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
+    MM_TRY(norm_split(w.y2, 512, w.sc2, w.sh2, 512, rows, NM, nullptr, 0, w.xp, 512, st));
+    p.bias = W[MMMOT_W_AF_B3]; p.M = 128;
+    p.Y = w.y3; p.y_ms = 128;
+    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W3P], wts->tc_scale[MMMOT_W_AF_W3P], st, tc::OUT_CL));
+    MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st, 2));
+    MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
+  } else {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W2T]; p.bias = W[MMMOT_W_AF_B2]; p.ldw = 512; p.M = 512; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.X = w.y01; p.x_gs = 1024L * NM; p.x_ks = NM; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.y2; p.y_gs = 512L * NM; p.y_ms = NM;
     p.part = w.part;
-    MM_TRY(run_layer<XM_NORM_RELU>(p, wts, MMMOT_W_AF_W2P, use_tc, st));
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
     p.Wt = W[MMMOT_W_AF_W3T]; p.bias = W[MMMOT_W_AF_B3]; p.ldw = 128; p.M = 128;
     p.X = w.y2; p.x_gs = 512L * NM; p.sc = w.sc2; p.sh = w.sh2;
     p.Y = w.y3; p.y_gs = 128L * NM;
-    MM_TRY(run_layer<XM_NORM_RELU>(p, wts, MMMOT_W_AF_W3P, use_tc, st));
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   }
   float* zdst = softmax_mode == MMMOT_SM_NONE ? link : w.z;
-  link_logit_kernel<<<mm_cdiv((long)G * NM, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
-                                                               W[MMMOT_W_AF_B4], G, NM, zdst);
+  if (use_tc) {
+    link_logit_cl_kernel<<<mm_cdiv((long)G * NM * 8, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
+                                                                        W[MMMOT_W_AF_B4], (long)G * NM, NM, zdst);
+  } else {
+    link_logit_kernel<<<mm_cdiv((long)G * NM, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
+                                                                 W[MMMOT_W_AF_B4], G, NM, zdst);
+  }
   MM_LAUNCH_CHECK();
   if (softmax_mode != MMMOT_SM_NONE) {
     softmax_stats_kernel<<<mm_cdiv((long)G * (n + m) * 32, 256), 256, 0, st>>>(w.z, G, n, m, w.rmax, w.rsum,

@@ -176,7 +176,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       p.H = h; p.W = w;
       p.S = n_img * h * w;
       p.X = (const float*)cur;
-      p.Y = buf[which];
+      p.Y = buf[which]; p.y_ms = p.M;
       p.relu = 1;
       p.tiles_per_group = mm_cdiv(p.S, tc::BN);
       p.num_tiles = p.tiles_per_group;
@@ -184,8 +184,8 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       const float wsc = wts->tc_scale[MMMOT_W_VGG_WP0 + i];
       const bool timed = mm_timing_on();
       if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
-      if (i == 0) MM_TRY(gemm_tc_launch<XM_CONV3>(p, wp, wsc, st, 1));     // fp32 NCHW crops in
-      else MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, 1));
+      if (i == 0) MM_TRY(gemm_tc_launch<XM_CONV3>(p, wp, wsc, st, tc::OUT_PACKED));     // fp32 NCHW crops in
+      else MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, tc::OUT_PACKED));
       if (timed) mm_timing_end(st);
       cur = buf[which]; which ^= 1;
       if (kPoolAfter[i]) {

@@ -10,10 +10,11 @@
 // miss the 1e-4 parity bound, and a BF16 hi/lo split is ~8x less accurate than this.
 //
 // Persistent, warp-specialised CTA (one per SM), tile 256 (M) x 256 (N), K chunks of 32:
-//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = output channel), bias / addend /
-//               ReLU, per-thread GroupNorm partial sums (no shuffles); fp32 [C][S] outputs are
-//               transposed through a per-warp smem scratch so every store is a full 128-byte line;
-//               conv outputs go out as packed FP16 (hi|lo) NHWC words, also 128 bytes per warp
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = output channel; warp w owns TMEM
+//               lanes 32*w..), bias / addend / ReLU, per-thread GroupNorm
+//               partial sums (no shuffles).  Outputs are channels-last ([column][channel]: fp32, or
+//               packed FP16 hi|lo words for the next tensor-core layer), so a warp's 32 channels
+//               make one 128-byte store; the legacy fp32 [C][S] layout is transposed through smem.
 //   warp  4     MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16), 12 per
 //               chunk; accumulators (2 x 256 fp32 columns) live in TMEM; owns TMEM alloc/dealloc
 //   warp  5     A loader: one thread, cp.async.bulk (TMA engine, no tensor map) of pre-packed
@@ -21,8 +22,9 @@
 //   warps 6-13  B producers: generate the operand tile (plain load / GroupNorm+ReLU of the
 //               producer layer / pairwise op / 3x3 im2col), split to FP16 hi/lo and write it to
 //               shared memory in the UMMA canonical K-major (no-swizzle) core-matrix layout.
-//               XM_CONV3S reads activations already stored as packed FP16 (hi|lo) NHWC words by the
-//               previous conv's epilogue: 128-bit loads, byte-permute de-interleave, no conversion.
+//               XM_CONV3S / XM_PACKED read activations already stored as packed FP16 (hi|lo)
+//               channels-last words (by the previous layer's epilogue or by the GroupNorm+ReLU
+//               split pass): 128-bit loads, byte-permute de-interleave, no conversion.
 // 3-stage smem ring (64 KB per stage), mbarrier full/empty pipeline, tcgen05.commit releases stages.
 #pragma once
 #include "gemm_simt.cuh"
@@ -37,7 +39,8 @@ constexpr int A_SUB = 2 * A_HALF;             // hi | lo
 constexpr int B_HALF = BN * BK * 2;           // 16 KB
 constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_HALF;   // 64 KB
 constexpr int A_LBO = 16 * 128, B_LBO = 32 * 128, SBO = 128;
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_THREADS = 448;   // 4 epilogue + 1 MMA + 1 loader + 8 producer warps (128 regs/thread)
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5;
 constexpr int PRODUCER_T0 = 192;   // first producer thread
 constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose scratch, one 32x33 fp32 block per warp
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + SCRATCH_BYTES;
@@ -122,6 +125,10 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
+enum { OUT_CS = 0,        // fp32 Y[g][co][s]   (legacy layout of the FP32 engine; transposed through smem)
+       OUT_PACKED = 1,    // uint32 Y[row][M] packed FP16 (hi | lo << 16), row = g*y_gs + column
+       OUT_CL = 2 };      // fp32  Y[row][y_ms] channels-last, row = g*y_gs + column
+
 struct TcP {
   GemmP g;             // same fields as the FP32 engine (tile width is tc::BN here)
   const uint4* Wp;     // packed weights: [kchunk][m128 tile][hi|lo][kgroup 4][m8 16][8 rows][8 k] f16
@@ -129,7 +136,7 @@ struct TcP {
   int k_chunks;        // ceil(K / 32)
   int mt_per_cta;      // 1 or 2 (128-row subtiles per CTA tile)
   float out_scale;     // 2^-s: undoes the power-of-two pre-scaling of the packed weights
-  int out_packed;      // 1: Y is uint32 NHWC [column][M] of packed FP16 (hi | lo << 16) words
+  int out_mode;        // OUT_*
   int dbg;             // profiling experiments only (mmmot_set_debug): 1 skip epilogue work, 2 skip A loads,
                        // 4 skip B generation, 8 skip MMA issue
 };
@@ -146,6 +153,18 @@ __device__ __forceinline__ uint32_t pack_split_f16(float x) {
       : "=r"(r)
       : "f"(x));
   return r;
+}
+
+template <bool RELU>
+__device__ __forceinline__ void epi_fast(uint32_t (&v)[32], float scale, float bv, float& s1, float& s2) {
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    float x = fmaf(__uint_as_float(v[j]), scale, bv);
+    if (RELU) x = fmaxf(x, 0.f);
+    v[j] = __float_as_uint(x);
+    s1 += x;
+    s2 = fmaf(x, x, s2);
+  }
 }
 
 template <int MODE>
@@ -175,10 +194,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       mbar_init(empty_bar(s), 1);  // tcgen05.commit
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);
+    mbar_init(tempty_bar, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512)
                  : "memory");
@@ -189,8 +208,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < EPI_WARPS) {
     // =============================== EPILOGUE ===============================
+    const int q = warp & 3;   // TMEM lane quadrant owned by this warp
     uint32_t tphase = 0;
     float* sc = scratch + warp * (32 * 33);
     uint32_t* ypk = reinterpret_cast<uint32_t*>(p.Y);
@@ -204,45 +224,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       tphase ^= 1;
       tc_fence_after();
       for (int mt = 0; mt < MT; mt++) {
-        const int co_base = (mg * MT + mt) * 128 + warp * 32;
+        const int co_base = (mg * MT + mt) * 128 + q * 32;
         const int co = co_base + lane;
         const bool rowok = co < p.M;
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
+        for (int half = 0; half < 2; half++) {
         double d1 = 0.0, d2 = 0.0;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; cc++) {
-          if (cc * 32 >= len) break;   // warp-uniform
+        for (int cc = 0; cc < 4; cc++) {
+          const int col0 = half * 128 + cc * 32;
+          if (col0 >= len) break;   // warp-uniform
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * 256 + cc * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
           if (P.dbg & 1) continue;
           float s1 = 0.f, s2 = 0.f;
+          if (col0 + 32 <= len && !p.addend) {
+            if (p.relu) epi_fast<true>(v, P.out_scale, bv, s1, s2);
+            else epi_fast<false>(v, P.out_scale, bv, s1, s2);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float x = fmaf(__uint_as_float(v[j]), P.out_scale, bv);
-            const int col = cc * 32 + j;
-            if (p.addend && rowok && col < len)
-              x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
-            if (p.relu) x = fmaxf(x, 0.f);
-            v[j] = __float_as_uint(x);
-            if (col < len) { s1 += x; s2 += x * x; }
+            for (int j = 0; j < 32; j++) {
+              float x = fmaf(__uint_as_float(v[j]), P.out_scale, bv);
+              const int col = col0 + j;
+              if (p.addend && rowok && col < len)
+                x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[j] = __float_as_uint(x);
+              if (col < len) { s1 += x; s2 = fmaf(x, x, s2); }
+            }
           }
           d1 += (double)s1; d2 += (double)s2;
           if (!p.Y) continue;
-          if (P.out_packed) {
-            // NHWC packed FP16 (hi|lo): word [column][channel]; a warp writes 32 consecutive channels
-            if (rowok) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const int col = cc * 32 + j;
-                if (col < len) ypk[(long)(c0 + col) * p.M + co] = pack_split_f16(__uint_as_float(v[j]));
-              }
-            }
-          } else {
+          if (P.out_mode == OUT_CS) {
             // fp32 [C][S]: transpose the 32x32 block through smem so each store is one 128-byte line
 #pragma unroll
             for (int j = 0; j < 32; j++) sc[lane * 33 + j] = __uint_as_float(v[j]);
             __syncwarp();
-            const int col = cc * 32 + lane;
+            const int col = col0 + lane;
             if (col < len) {
               float* dst = p.Y + (long)g * p.y_gs + (long)co_base * p.y_ms + c0 + col;
               const int rmax = min(32, p.M - co_base);
@@ -250,15 +268,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
               for (int r = 0; r < rmax; r++) dst[(long)r * p.y_ms] = sc[r * 33 + lane];
             }
             __syncwarp();
+          } else if (rowok) {
+            // channels-last: a warp's 32 consecutive channels of one column = one 128-byte store
+            const int nvalid = min(32, len - col0);
+            if (P.out_mode == OUT_PACKED) {
+              uint32_t* dst = ypk + ((long)g * p.y_gs + c0 + col0) * p.y_ms + co;
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < nvalid) dst[(long)j * p.y_ms] = pack_split_f16(__uint_as_float(v[j]));
+            } else {
+              float* dst = p.Y + ((long)g * p.y_gs + c0 + col0) * p.y_ms + co;
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < nvalid) dst[(long)j * p.y_ms] = __uint_as_float(v[j]);
+            }
           }
         }
-        if (p.part && rowok) p.part[(long)nt * p.M + co] = make_double2(d1, d2);
+        // two statistics partials per tile (one per column half), reduced in fixed order afterwards
+        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2(d1, d2);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == LOAD_WARP) {
     // =============================== A LOADER ===============================
     if (lane == 0) {
       uint32_t it = 0;
@@ -333,40 +367,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       if (lane == 0) mbar_arrive(full_bar(s));
     };
 
-    if (MODE == XM_CONV3S) {
-      // ---- packed-FP16 NHWC activations: item = (pixel, k-group of 8 channels) = 32 contiguous bytes ----
+    if (MODE == XM_CONV3S || MODE == XM_PACKED) {
+      // ---- packed-FP16 channels-last activations: item = (row, k-group of 8 channels) = 32 contiguous bytes.
+      //      XM_CONV3S: rows are NHWC pixels, 9 taps (K order k = tap*Cin + ci, Cin % 32 == 0)
+      //      XM_PACKED: rows are columns of X[row][Cin words], one tap (K <= Cin, K % 32 == 0)
       const uint32_t* X = reinterpret_cast<const uint32_t*>(p.X);
       const int kg = pt & 3;
-      long pbase[4];   // word offset of (img, y, x, channel 0) for this thread's 4 pixels
-      int pmask[4];    // 9-bit tap validity
+      long pbase[4];   // word offset of this thread's 4 rows
+      int pmask[4];    // tap validity bits
       auto gather = [&](uint4 (&w)[8]) {
         if (gi >= my_chunks) { gi++; return; }
         const int kc = (int)(gi % KC);
         if (kc == 0) {
           int g, c0, len;
           tile_cols(gi, g, c0, len);
-          const int hw = p.H * p.W;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             const int pl = (pt >> 2) + 64 * i;
-            const int s = c0 + pl;
-            const int img = s / hw, pix = s - img * hw;
-            const int y = pix / p.W, x = pix - y * p.W;
-            pbase[i] = (long)s * p.Cin;
-            int mk = 0;
+            if (MODE == XM_CONV3S) {
+              const int hw = p.H * p.W;
+              const int s = c0 + pl;
+              const int img = s / hw, pix = s - img * hw;
+              const int y = pix / p.W, x = pix - y * p.W;
+              pbase[i] = (long)s * p.Cin;
+              int mk = 0;
 #pragma unroll
-            for (int tp = 0; tp < 9; tp++) {
-              const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-              if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) mk |= 1 << tp;
+              for (int tp = 0; tp < 9; tp++) {
+                const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) mk |= 1 << tp;
+              }
+              pmask[i] = pl < len ? mk : 0;
+            } else {
+              pbase[i] = ((long)g * p.x_gs + c0 + pl) * p.Cin;
+              pmask[i] = pl < len ? 1 : 0;
             }
-            pmask[i] = pl < len ? mk : 0;
           }
         }
         gi++;
         if (P.dbg & 4) return;
         const int k0 = kc * BK;
-        const int tap = k0 / p.Cin, ci0 = k0 - tap * p.Cin;     // K order: k = tap*Cin + ci, Cin % 32 == 0
-        const long d = (long)((tap / 3 - 1) * p.W + (tap % 3 - 1)) * p.Cin + ci0 + kg * 8;
+        int tap = 0;
+        long d = k0 + kg * 8;
+        if (MODE == XM_CONV3S) {
+          tap = k0 / p.Cin;
+          d = (long)((tap / 3 - 1) * p.W + (tap % 3 - 1)) * p.Cin + (k0 - tap * p.Cin) + kg * 8;
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           if ((pmask[i] >> tap) & 1) {
@@ -522,7 +567,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
@@ -530,9 +575,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
 }  // namespace tc
 
 // Host launcher.  `Wp` = weights packed by mmmot_b200/weights.py::pack_tc; out_scale = 2^-s of that packing.
-// out_packed: write Y as packed FP16 (hi|lo) NHWC words (conv layers) instead of fp32 [C][S].
+// GroupNorm partials: TWO per column tile (p.part[(tile*2 + half)*M + co]) -> stats_reduce(..., mult = 2).
 template <int MODE>
-static int gemm_tc_launch(const GemmP& g, const uint4* Wp, float out_scale, cudaStream_t st, int out_packed = 0) {
+static int gemm_tc_launch(const GemmP& g, const uint4* Wp, float out_scale, cudaStream_t st,
+                          int out_mode = tc::OUT_CS) {
   if (!Wp || g.num_tiles <= 0) return MMMOT_E_ARG;
   static int sms = 0;
   if (!sms) {
@@ -553,7 +599,7 @@ static int gemm_tc_launch(const GemmP& g, const uint4* Wp, float out_scale, cuda
   P.k_chunks = (g.K + tc::BK - 1) / tc::BK;
   P.mt_per_cta = P.m_tiles >= 2 ? 2 : 1;
   P.out_scale = out_scale;
-  P.out_packed = out_packed;
+  P.out_mode = out_mode;
   P.dbg = mm_debug_flags();
   const long mgroups = (P.m_tiles + P.mt_per_cta - 1) / P.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;

@@ -12,12 +12,14 @@
 // Fixed-order reduction of the contraction engine's per-tile partials: stats[g][c] = sum over the
 // group's tiles (ascending) of part[tile][c].  Group g owns tiles [g*tpg, (g+1)*tpg) (uniform) or
 // [gstart[g], gstart[g+1]) (table tiling).
+// `mult` = partials per tile (1 for the FP32 engine, 2 for the tcgen05 engine).
 static __global__ void stats_reduce_kernel(const double2* __restrict__ part, int M, int G, int tpg,
-                                           const int* __restrict__ gstart, double* __restrict__ stats) {
+                                           const int* __restrict__ gstart, int mult,
+                                           double* __restrict__ stats) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= G * M) return;
   int g = idx / M, c = idx - g * M;
-  int t0 = gstart ? gstart[g] : g * tpg, t1 = gstart ? gstart[g + 1] : (g + 1) * tpg;
+  int t0 = (gstart ? gstart[g] : g * tpg) * mult, t1 = (gstart ? gstart[g + 1] : (g + 1) * tpg) * mult;
   double s1 = 0.0, s2 = 0.0;
   for (int t = t0; t < t1; t++) {
     double2 v = part[(long)t * M + c];
@@ -29,8 +31,8 @@ static __global__ void stats_reduce_kernel(const double2* __restrict__ part, int
 }
 
 static inline int stats_reduce(const double2* part, int M, int G, int tpg, const int* gstart, double* stats,
-                               cudaStream_t st) {
-  stats_reduce_kernel<<<mm_cdiv((long)G * M, 128), 128, 0, st>>>(part, M, G, tpg, gstart, stats);
+                               cudaStream_t st, int mult = 1) {
+  stats_reduce_kernel<<<mm_cdiv((long)G * M, 128), 128, 0, st>>>(part, M, G, tpg, gstart, mult, stats);
   MM_LAUNCH_CHECK();
   return 0;
 }

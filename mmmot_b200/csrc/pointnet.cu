@@ -8,8 +8,8 @@
 // Per-detection pooling is a MEAN.  One frame-pair = one GroupNorm domain.
 #include <vector>
 
-#include "gemm_tc.cuh"
 #include "norm_ops.cuh"
+#include "tc_ops.cuh"
 
 namespace {
 
@@ -65,8 +65,25 @@ __global__ void pointnet_out_kernel(const float* __restrict__ O, const float* __
   feats[(((long)pair * 3 + 1) * 512 + c) * L + l] = v;
 }
 
+// channels-last variant: Y[p][C]; one CTA per detection, threads over channels (coalesced), points in order
+// -> out[c][d] (channel-major, consumed by the FP32 engine's small contractions).
+__global__ void segment_mean_cl_kernel(const float* __restrict__ Y, int C, const int* __restrict__ split,
+                                       const float* __restrict__ sc, const float* __restrict__ sh, int ndet,
+                                       int L, float* __restrict__ out) {
+  const int d = blockIdx.x;
+  const int pair = d / L;
+  const int s = split[d], e = split[d + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = sc[(long)pair * C + c], b = sh[(long)pair * C + c];
+    float acc = 0.f;
+    for (int p = s; p < e; p++) acc += fmaxf(fmaf(Y[(long)p * C + c], a, b), 0.f);
+    out[(long)c * ndet + d] = e > s ? acc / (float)(e - s) : 0.f;
+  }
+}
+
 struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *hmean, *o;
+  uint32_t *x1p, *xp;   // tensor-core path: packed FP16 (hi|lo) normalised activations [P][64], [P][128]
   float *sc1, *sh1, *sc, *sh;
   double* stats;
   double2* part;
@@ -82,6 +99,8 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
   w.t0 = a.take<float>(128 * P);
   w.t1 = a.take<float>(64 * P);
   w.big = a.take<float>(1024 * P);
+  w.x1p = a.take<uint32_t>(64 * P);
+  w.xp = a.take<uint32_t>(128 * P);
   w.gmean = a.take<float>(1024 * nd);
   w.u = a.take<float>(512 * nd);
   w.hmean = a.take<float>(512 * nd);
@@ -103,7 +122,7 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
 
 extern "C" size_t mmmot_pointnet_workspace(int pairs, int L, long p_total) {
   MmArena a(nullptr, 0);
-  carve(a, pairs, L, p_total, p_total / 128 + pairs + 1);
+  carve(a, pairs, L, p_total, p_total / 128 + 2 * pairs + 2);
   return a.off;
 }
 
@@ -131,7 +150,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     for (int c = s; c < e; c += TNW) tiles.push_back(make_int4(p, c, min(TNW, e - c), 0));
   }
   gstart[pairs] = (int)tiles.size();
-  const long max_tiles = P / 128 + pairs + 1;
+  const long max_tiles = P / 128 + 2 * pairs + 2;   // also bounds 2 partials per 256-wide tile
   MmArena ar(workspace, workspace_bytes);
   PnWs w = carve(ar, pairs, L, P, max_tiles);
   if (!ar.ok() || (long)tiles.size() > max_tiles) return MMMOT_E_WORKSPACE;
@@ -144,8 +163,60 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   point_segment_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(det_split, ndet, P, w.seg);
   MM_LAUNCH_CHECK();
 
-  // trunk: 3 -> 64 -> 64 -> 64 -> 128 -> 1024, each conv + GroupNorm(C,C) over the pair's points + ReLU
   const int cin[5] = {3, 64, 64, 64, 128}, cout[5] = {64, 64, 64, 128, 1024};
+  if (use_tc) {
+    // ---------------- tensor-core path: channels-last activations ----------------
+    // layer i writes fp32 Y[p][cout] + GroupNorm partials; norm_split turns it into the packed FP16
+    // operand of layer i+1.  y1's packed form (x1p) is kept for the head.
+    float* ybuf[5] = {w.y1, w.t0, w.t1, w.t0, w.big};
+    for (int i = 0; i < 5; i++) {
+      const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
+      GemmP p = gemm_defaults();
+      p.bias = q[1]; p.M = cout[i]; p.K = cin[i];
+      p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+      p.Y = ybuf[i]; p.y_ms = cout[i];
+      p.part = w.part;
+      const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
+      const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
+      if (i == 0) {
+        p.X = w.xt; p.x_ks = P;                                 // fp32 [3][P] gather
+        MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st, tc::OUT_CL));
+      } else {
+        p.X = (const float*)(i == 1 ? w.x1p : w.xp); p.Cin = cin[i];   // packed [P][cin]
+        MM_TRY(gemm_tc_launch<XM_PACKED>(p, wp, wps, st, tc::OUT_CL));
+      }
+      MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
+      MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
+      if (i < 4)
+        MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, cout[i], st));
+    }
+    segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 1024, det_split, w.sc, w.sh, ndet, L, w.gmean);
+    MM_LAUNCH_CHECK();
+    {
+      GemmP p = gemm_defaults();
+      p.Wt = wts->w[MMMOT_W_PN_WHGT]; p.ldw = 512; p.M = 512; p.K = 1024;
+      p.S = ndet; p.tiles_per_group = mm_cdiv(ndet, 128); p.num_tiles = p.tiles_per_group;
+      p.X = w.gmean; p.x_ks = ndet;
+      p.Y = w.u; p.y_ms = ndet;
+      MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+    }
+    {
+      GemmP p = gemm_defaults();
+      p.bias = wts->w[MMMOT_W_PN_BH]; p.M = 512; p.K = 64;
+      p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+      p.X = (const float*)w.x1p; p.Cin = 64;
+      p.Y = w.big; p.y_ms = 512;
+      p.part = w.part;
+      p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
+      MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], st,
+                                       tc::OUT_CL));
+      MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));
+      MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1, w.sc, w.sh, st));
+      segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 512, det_split, w.sc, w.sh, ndet, L, w.hmean);
+      MM_LAUNCH_CHECK();
+    }
+  } else {
+  // trunk: 3 -> 64 -> 64 -> 64 -> 128 -> 1024, each conv + GroupNorm(C,C) over the pair's points + ReLU
   const float* src[5] = {w.xt, w.y1, w.t0, w.t1, w.t0};
   float* dst[5] = {w.y1, w.t0, w.t1, w.t0, w.big};
   for (int i = 0; i < 5; i++) {
@@ -156,16 +227,12 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.X = src[i]; p.x_ks = P;
     p.Y = dst[i]; p.y_ms = P;
     p.part = w.part;
-    const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
-    const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
     if (i == 0) {
-      if (use_tc) MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st));
-      else MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+      MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
     } else {
       p.sc = (i == 1) ? w.sc1 : w.sc;
       p.sh = (i == 1) ? w.sh1 : w.sh;
-      if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, wp, wps, st));
-      else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+      MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     }
     MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, i == 0 ? w.sc1 : w.sc,
@@ -193,14 +260,14 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     p.Y = w.big; p.y_ms = P;
     p.part = w.part;
     p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
-    if (use_tc) MM_TRY(gemm_tc_launch<XM_NORM_RELU>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], st));
-    else MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
+    MM_TRY(gemm_simt_launch<XM_NORM_RELU>(p, st));
     MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st));
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,
                        w.sc, w.sh, st));
     segment_mean_kernel<<<mm_cdiv(512L * ndet * 32, 256), 256, 0, st>>>(w.big, P, det_split, w.sc, w.sh,
                                                                         512, ndet, L, w.hmean);
     MM_LAUNCH_CHECK();
+  }
   }
   // conv2 512 -> 512 over the pair's L detections, GroupNorm(16,512), ReLU (point_net.py:40-41)
   {
