@@ -197,7 +197,8 @@ __global__ void softmax_apply_kernel(const float* __restrict__ z, int mode, int 
 
 struct AfWs {
   float *y01, *y2, *y3, *z;
-  uint32_t* xp;   // tensor-core path: packed FP16 (hi|lo) normalised activations [G*NM][512]
+  uint32_t* xp;   // tensor-core path: packed FP16 (hi|lo) operands [G*NM][512]
+  float* fcl;     // tensor-core path: channels-last copy of the feature stacks [G][L][512]
   float *sc1, *sh1, *sc0, *sh0, *sc2, *sh2, *sc3, *sh3;
   float *v, *h1, *h2, *nsc1, *nsh1, *nsc2, *nsh2;
   float *rmax, *rsum, *cmax, *csum;
@@ -214,6 +215,7 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.y3 = a.take<float>(G * 128 * NM);
   w.z = a.take<float>(G * NM);
   w.xp = a.take<uint32_t>(G * NM * 512);
+  w.fcl = a.take<float>(G * (n + m) * 512);
   w.sc1 = a.take<float>(G * 512); w.sh1 = a.take<float>(G * 512);
   w.sc0 = a.take<float>(G * 512); w.sh0 = a.take<float>(G * 512);
   w.sc2 = a.take<float>(G * 512); w.sh2 = a.take<float>(G * 512);
@@ -231,11 +233,6 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.part = a.take<double2>(G * 2 * mm_cdiv(NM, 256) * 1024);   // covers 1 partial per 128-tile and 2 per 256-tile
   w.npart = a.take<double2>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);
   return w;
-}
-
-template <int MODE>
-int run_layer(GemmP& p, const mmmot_weights* wts, int wid, bool use_tc, int out_mode, cudaStream_t st) {
-  return use_tc ? gemm_tc_launch<MODE>(p, (const uint4*)wts->w[wid], wts->tc_scale[wid], st, out_mode) : gemm_simt_launch<MODE>(p, st);
 }
 
 }  // namespace
@@ -265,18 +262,33 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor.
   // FP32 engine: y01[g][1024][NM].  Tensor-core engine: channels-last y01[g*NM + s][1024].
   const int pm = use_tc ? 2 : 1;   // GroupNorm partials per column tile
-  {
+  if (use_tc) {
+    // pairwise operand emitted once as packed FP16 words (coalesced float4 in / uint4 out), then a plain
+    // packed-operand contraction
+    const long rows = (long)G * NM;
+    MM_TRY(transpose_f32(feats, w.fcl, 512, L, G, st));
+    const int nb = mm_cdiv(rows * 128, 256);
+    if (affinity_op == MMMOT_AFF_MULTIPLY) pair_split_kernel<MMMOT_AFF_MULTIPLY><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
+    else if (affinity_op == MMMOT_AFF_MINUS_ABS) pair_split_kernel<MMMOT_AFF_MINUS_ABS><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
+    else pair_split_kernel<MMMOT_AFF_MINUS><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
+    MM_LAUNCH_CHECK();
+    GemmP p = gemm_defaults();
+    p.bias = W[MMMOT_W_AF_B01]; p.M = 1024; p.K = 512;
+    p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
+    p.X = (const float*)w.xp; p.Cin = 512; p.x_gs = NM;
+    p.Y = w.y01; p.y_gs = NM; p.y_ms = 1024;
+    p.part = w.part;
+    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W01P], wts->tc_scale[MMMOT_W_AF_W01P], st, tc::OUT_CL));
+  } else {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.X = feats; p.n = n; p.m = m; p.Lf = L;
-    p.Y = w.y01;
-    if (use_tc) { p.y_gs = NM; p.y_ms = 1024; } else { p.y_gs = 1024L * NM; p.y_ms = NM; }
+    p.Y = w.y01; p.y_gs = 1024L * NM; p.y_ms = NM;
     p.part = w.part;
-    const int om = tc::OUT_CL;
-    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? run_layer<XM_PAIR_MUL>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st)
-            : affinity_op == MMMOT_AFF_MINUS_ABS ? run_layer<XM_PAIR_ABS>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st)
-                                                 : run_layer<XM_PAIR_SUB>(p, wts, MMMOT_W_AF_W01P, use_tc, om, st);
+    int r = affinity_op == MMMOT_AFF_MULTIPLY    ? gemm_simt_launch<XM_PAIR_MUL>(p, st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS ? gemm_simt_launch<XM_PAIR_ABS>(p, st)
+                                                 : gemm_simt_launch<XM_PAIR_SUB>(p, st);
     if (r) return r;
   }
   // statistics are [G][1024]: channels 0..511 = conv1.0 -> GroupNorm(512,512) (per channel over N x M),

@@ -84,6 +84,52 @@ __global__ void plane_mean_packed_kernel(const uint32_t* __restrict__ in, float*
   out[idx] = s / (float)hw;
 }
 
+// First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound:
+// 1 MB of output per crop), so a direct FP32 FFMA kernel writes the packed FP16 (hi|lo) NHWC words the next
+// layer's operand producers expect.  64 pixels x 4 channel groups (16 channels) per CTA; weights in smem.
+// wt: [(ky*3+kx)*3 + ci][64] (BN folded), ReLU fused.
+__global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, long n_pix, int H, int W,
+                                                           uint32_t* __restrict__ out) {
+  __shared__ float ws[27 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long pix = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = (threadIdx.x & 3) * 16;
+  if (pix >= n_pix) return;
+  const int hw = H * W;
+  const long img = pix / hw;
+  const int r = (int)(pix - img * hw), y = r / W, x = r - y * W;
+  const float* src = in + img * 3 * hw;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; c++) acc[c] = bs[cg + c];
+#pragma unroll
+  for (int tap = 0; tap < 9; tap++) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++) {
+      const float v = ok ? __ldg(src + (long)ci * hw + yy * W + xx) : 0.f;
+      const float* wr = ws + (tap * 3 + ci) * 64 + cg;
+#pragma unroll
+      for (int c = 0; c < 16; c++) acc[c] = fmaf(v, wr[c], acc[c]);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint4 o;
+    o.x = tc::pack_split_f16(fmaxf(acc[4 * q], 0.f));
+    o.y = tc::pack_split_f16(fmaxf(acc[4 * q + 1], 0.f));
+    o.z = tc::pack_split_f16(fmaxf(acc[4 * q + 2], 0.f));
+    o.w = tc::pack_split_f16(fmaxf(acc[4 * q + 3], 0.f));
+    dst[q] = o;
+  }
+}
+
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
   // 128 threads (4 warps)
 #pragma unroll
@@ -184,8 +230,13 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       const float wsc = wts->tc_scale[MMMOT_W_VGG_WP0 + i];
       const bool timed = mm_timing_on();
       if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
-      if (i == 0) MM_TRY(gemm_tc_launch<XM_CONV3>(p, wp, wsc, st, tc::OUT_PACKED));     // fp32 NCHW crops in
-      else MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, tc::OUT_PACKED));
+      if (i == 0) {
+        conv0_packed_kernel<<<mm_cdiv(p.S, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
+                                                             (long)p.S, h, w, (uint32_t*)buf[which]);
+        MM_LAUNCH_CHECK();
+      } else {
+        MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, tc::OUT_PACKED));
+      }
       if (timed) mm_timing_end(st);
       cur = buf[which]; which ^= 1;
       if (kPoolAfter[i]) {

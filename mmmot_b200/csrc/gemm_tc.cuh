@@ -238,16 +238,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
           if (P.dbg & 1) continue;
           float s1 = 0.f, s2 = 0.f;
-          if (col0 + 32 <= len && !p.addend) {
-            if (p.relu) epi_fast<true>(v, P.out_scale, bv, s1, s2);
-            else epi_fast<false>(v, P.out_scale, bv, s1, s2);
+          bool fast = col0 + 32 <= len;
+          float bva = bv;
+          if (fast && p.addend) {
+            // per-detection addend, channels-last addend[det][M]: points of one detection are contiguous, so
+            // a 32-column chunk almost always lies inside one detection -> fold the addend into the bias
+            const int da = __ldg(p.seg + c0 + col0), db = __ldg(p.seg + c0 + col0 + 31);
+            if (da == db) { if (rowok) bva += __ldg(p.addend + (long)da * p.ld_add + co); }
+            else fast = false;
+          }
+          if (fast) {
+            if (p.relu) epi_fast<true>(v, P.out_scale, bva, s1, s2);
+            else epi_fast<false>(v, P.out_scale, bva, s1, s2);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) {
               float x = fmaf(__uint_as_float(v[j]), P.out_scale, bv);
               const int col = col0 + j;
               if (p.addend && rowok && col < len)
-                x += __ldg(p.addend + (long)co * p.ld_add + __ldg(p.seg + c0 + col));
+                x += __ldg(p.addend + (long)__ldg(p.seg + c0 + col) * p.ld_add + co);
               if (p.relu) x = fmaxf(x, 0.f);
               v[j] = __float_as_uint(x);
               if (col < len) { s1 += x; s2 = fmaf(x, x, s2); }

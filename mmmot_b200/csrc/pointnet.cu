@@ -82,7 +82,7 @@ __global__ void segment_mean_cl_kernel(const float* __restrict__ Y, int C, const
 }
 
 struct PnWs {
-  float *xt, *y1, *t0, *t1, *big, *gmean, *u, *hmean, *o;
+  float *xt, *y1, *t0, *t1, *big, *gmean, *u, *ut, *hmean, *o;
   uint32_t *x1p, *xp;   // tensor-core path: packed FP16 (hi|lo) normalised activations [P][64], [P][128]
   float *sc1, *sh1, *sc, *sh;
   double* stats;
@@ -103,6 +103,7 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
   w.xp = a.take<uint32_t>(128 * P);
   w.gmean = a.take<float>(1024 * nd);
   w.u = a.take<float>(512 * nd);
+  w.ut = a.take<float>(512 * nd);
   w.hmean = a.take<float>(512 * nd);
   w.o = a.take<float>(512 * nd);
   w.sc1 = a.take<float>((size_t)pairs * 64);
@@ -199,6 +200,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       p.X = w.gmean; p.x_ks = ndet;
       p.Y = w.u; p.y_ms = ndet;
       MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
+      MM_TRY(transpose_f32(w.u, w.ut, 512, ndet, 1, st));     // -> [det][512] for coalesced epilogue reads
     }
     {
       GemmP p = gemm_defaults();
@@ -207,7 +209,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       p.X = (const float*)w.x1p; p.Cin = 64;
       p.Y = w.big; p.y_ms = 512;
       p.part = w.part;
-      p.addend = w.u; p.seg = w.seg; p.ld_add = ndet;
+      p.addend = w.ut; p.seg = w.seg; p.ld_add = 512;
       MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], st,
                                        tc::OUT_CL));
       MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));

@@ -34,3 +34,57 @@ static inline int norm_split(const float* in, long ldi, const float* sc, const f
   MM_LAUNCH_CHECK();
   return 0;
 }
+
+// dst[g][col][row] = src[g][row][col]   (small matrices: feature stacks 512 x L, U 512 x ndet)
+static __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                                        int groups) {
+  __shared__ float tile[32][33];
+  const int g = blockIdx.z;
+  const float* s = src + (long)g * rows * cols;
+  float* d = dst + (long)g * rows * cols;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = s[(long)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) d[(long)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+static inline int transpose_f32(const float* src, float* dst, int rows, int cols, int groups, cudaStream_t st) {
+  dim3 grid(mm_cdiv(cols, 32), mm_cdiv(rows, 32), groups), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols, groups);
+  MM_LAUNCH_CHECK();
+  return 0;
+}
+
+// Pairwise operand of the affinity contraction (reference modules/gcn.py:6-41) emitted directly as packed
+// FP16 (hi|lo) channels-last words:  x[(g*N + i)*M + j][c] = f[g][i][c] (*|-) f[g][N + j][c], from the
+// channels-last feature stacks fcl[g][L][512].  (fp32 x is never stored; 4 B/element like fp32 but already
+// in the tensor-core operand format.)
+template <int OP>
+static __global__ void pair_split_kernel(const float* __restrict__ fcl, int n, int m, long rows,
+                                         uint32_t* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 128) return;
+  const long row = idx >> 7;
+  const int c = (int)(idx & 127) * 4;
+  const int nm = n * m, L = n + m;
+  const int g = (int)(row / nm);
+  const int r = (int)(row - (long)g * nm);
+  const int i = r / m, j = r - i * m;
+  const float4 a = *reinterpret_cast<const float4*>(fcl + ((long)g * L + i) * 512 + c);
+  const float4 b = *reinterpret_cast<const float4*>(fcl + ((long)g * L + n + j) * 512 + c);
+  float4 x;
+  if (OP == MMMOT_AFF_MULTIPLY) { x.x = a.x * b.x; x.y = a.y * b.y; x.z = a.z * b.z; x.w = a.w * b.w; }
+  else if (OP == MMMOT_AFF_MINUS_ABS) {
+    x.x = fabsf((a.x - b.x) * 0.5f); x.y = fabsf((a.y - b.y) * 0.5f);
+    x.z = fabsf((a.z - b.z) * 0.5f); x.w = fabsf((a.w - b.w) * 0.5f);
+  } else { x.x = (a.x - b.x) * 0.5f; x.y = (a.y - b.y) * 0.5f; x.z = (a.z - b.z) * 0.5f; x.w = (a.w - b.w) * 0.5f; }
+  uint4 o;
+  o.x = tc::pack_split_f16(x.x); o.y = tc::pack_split_f16(x.y);
+  o.z = tc::pack_split_f16(x.z); o.w = tc::pack_split_f16(x.w);
+  *reinterpret_cast<uint4*>(out + row * 512 + c) = o;
+}
