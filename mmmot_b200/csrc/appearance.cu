@@ -86,47 +86,70 @@ __global__ void plane_mean_packed_kernel(const uint32_t* __restrict__ in, float*
 
 // First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound:
 // 1 MB of output per crop), so a direct FP32 FFMA kernel writes the packed FP16 (hi|lo) NHWC words the next
-// layer's operand producers expect.  64 pixels x 4 channel groups (16 channels) per CTA; weights in smem.
-// wt: [(ky*3+kx)*3 + ci][64] (BN folded), ReLU fused.
+// layer's operand producers expect.  Each thread: 4 consecutive pixels x 16 channels (weights read from smem
+// once per 4 pixels as 128-bit loads); CTA = 64 pixel quads x 4 channel groups.  wt: [(ky*3+kx)*3 + ci][64]
+// (BN folded), ReLU fused.  W % 4 == 0.
 __global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
-                                                           const float* __restrict__ bias, long n_pix, int H, int W,
+                                                           const float* __restrict__ bias, long n_quads, int H, int W,
                                                            uint32_t* __restrict__ out) {
-  __shared__ float ws[27 * 64];
+  __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long pix = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const long quad = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
   const int cg = (threadIdx.x & 3) * 16;
-  if (pix >= n_pix) return;
-  const int hw = H * W;
-  const long img = pix / hw;
-  const int r = (int)(pix - img * hw), y = r / W, x = r - y * W;
+  if (quad >= n_quads) return;
+  const int wq = W >> 2, hw = H * W;
+  const long row = quad / wq;                // (img, y)
+  const int x0 = (int)(quad - row * wq) * 4;
+  const long img = row / H;
+  const int y = (int)(row - img * H);
   const float* src = in + img * 3 * hw;
-  float acc[16];
+  float acc[4][16];
 #pragma unroll
-  for (int c = 0; c < 16; c++) acc[c] = bs[cg + c];
+  for (int p = 0; p < 4; p++)
 #pragma unroll
-  for (int tap = 0; tap < 9; tap++) {
-    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    for (int c = 0; c < 16; c++) acc[p][c] = bs[cg + c];
 #pragma unroll
-    for (int ci = 0; ci < 3; ci++) {
-      const float v = ok ? __ldg(src + (long)ci * hw + yy * W + xx) : 0.f;
-      const float* wr = ws + (tap * 3 + ci) * 64 + cg;
+  for (int ci = 0; ci < 3; ci++) {
 #pragma unroll
-      for (int c = 0; c < 16; c++) acc[c] = fmaf(v, wr[c], acc[c]);
+    for (int ky = 0; ky < 3; ky++) {
+      const int yy = y + ky - 1;
+      const bool oky = yy >= 0 && yy < H;
+      const float* rowp = src + (long)ci * hw + (long)yy * W + x0;
+      float v[6];
+#pragma unroll
+      for (int t = 0; t < 6; t++) {
+        const int xx = x0 + t - 1;
+        v[t] = (oky && xx >= 0 && xx < W) ? __ldg(rowp + t - 1) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + cg);
+        float w[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const float4 t4 = wr[q]; w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w; }
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+          for (int c = 0; c < 16; c++) acc[p][c] = fmaf(v[p + kx], w[c], acc[p][c]);
+      }
     }
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + cg);
+  const long pix0 = row * W + x0;
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    uint4 o;
-    o.x = tc::pack_split_f16(fmaxf(acc[4 * q], 0.f));
-    o.y = tc::pack_split_f16(fmaxf(acc[4 * q + 1], 0.f));
-    o.z = tc::pack_split_f16(fmaxf(acc[4 * q + 2], 0.f));
-    o.w = tc::pack_split_f16(fmaxf(acc[4 * q + 3], 0.f));
-    dst[q] = o;
+  for (int p = 0; p < 4; p++) {
+    uint4* dst = reinterpret_cast<uint4*>(out + (pix0 + p) * 64 + cg);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      uint4 o;
+      o.x = tc::pack_split_f16(fmaxf(acc[p][4 * q], 0.f));
+      o.y = tc::pack_split_f16(fmaxf(acc[p][4 * q + 1], 0.f));
+      o.z = tc::pack_split_f16(fmaxf(acc[p][4 * q + 2], 0.f));
+      o.w = tc::pack_split_f16(fmaxf(acc[p][4 * q + 3], 0.f));
+      dst[q] = o;
+    }
   }
 }
 
@@ -231,8 +254,8 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       const bool timed = mm_timing_on();
       if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
       if (i == 0) {
-        conv0_packed_kernel<<<mm_cdiv(p.S, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
-                                                             (long)p.S, h, w, (uint32_t*)buf[which]);
+        conv0_packed_kernel<<<mm_cdiv(p.S / 4, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
+                                                                 (long)p.S / 4, h, w, (uint32_t*)buf[which]);
         MM_LAUNCH_CHECK();
       } else {
         MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, tc::OUT_PACKED));
