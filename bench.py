@@ -14,8 +14,9 @@ the assignment indices, inside the timed region.
 value : frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks).
 e2e   : same metric through the public API with HOST (pinned) inputs: H2D of crops/points and D2H
         of the assignment results inside the timed region.
-roofline: dominant kernel = the 3x3-conv contraction of the VGG trunk (83 % of the algorithmic
-        FLOPs), timed per launch with CUDA events on the launching stream (library hook).
+roofline: dominant kernel = tc::gemm_tc_kernel<XM_CONV3S>, the tcgen05 3x3-conv contraction of the VGG
+        trunk (12 launches per chunk, 83 % of the algorithmic FLOPs, ~56 % of the step), timed per launch
+        with CUDA events on the launching stream (library hook mmmot_timing_*).
 cpu_baseline / --impl reference: the oracle port of the reference's PyTorch-CPU path (the reference
         is pure Python and /root/reference does not exist on the GPU box) on all host cores.
 """
@@ -77,8 +78,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def oracle_pairs_per_s(n_pairs, threads):
-    """The reference's CPU path (oracle port of TrackingNet.forward + HiGHS restatement of the LP)."""
+def pick_cpu_threads():
+    """torch's intra-op scaling on many-core hosts is poor for these shapes (128 threads were 14x slower
+    than 8 on the GPU box); time one small frame-pair at a few thread counts and keep the fastest."""
+    from mmmot_b200.synthetic import synthetic_pair, synthetic_state_dict
+    from oracle import torch_ref
+    ncpu = os.cpu_count() or 1
+    sd = synthetic_state_dict(CFG["fusion"], seed=0)
+    dets, info, split = synthetic_pair(16, 16, 64, CFG["hw"], seed=0)
+    best, best_t = 1, float("inf")
+    for th in sorted({min(ncpu, t) for t in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(th)
+        torch_ref.forward(sd, dets, info, split, CFG["fusion"], CFG["affinity_op"], CFG["softmax_mode"], CFG["neg_threshold"])
+        t = time.perf_counter()
+        torch_ref.forward(sd, dets, info, split, CFG["fusion"], CFG["affinity_op"], CFG["softmax_mode"], CFG["neg_threshold"])
+        dt = time.perf_counter() - t
+        if dt < best_t:
+            best, best_t = th, dt
+    return best
+
+
+def oracle_pairs_per_s(n_pairs, threads, budget_s=150.0):
+    """The reference's CPU path (oracle port of TrackingNet.forward + HiGHS restatement of the LP).
+    Bounded sample: stops early once `budget_s` seconds of CPU work are spent (>= 1 pair is always timed)."""
     from mmmot_b200.synthetic import synthetic_pair, synthetic_state_dict
     from oracle import lp_ref, torch_ref
     torch.set_num_threads(threads)
@@ -91,6 +113,9 @@ def oracle_pairs_per_s(n_pairs, threads):
                                                    CFG["softmax_mode"], CFG["neg_threshold"])
         lp_ref.milp_solve(det[2], [link[0][2:3]], new[2], end[2], [CFG["n"], CFG["n"]])
         t_tot += time.perf_counter() - t
+        if t_tot > budget_s:
+            n_pairs = p + 1
+            break
     return n_pairs / t_tot, t_tot
 
 
@@ -105,16 +130,14 @@ def config_dict(pairs, world):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 0) and 1):           # one warm-up pair (page-in / thread pools)
-        oracle_pairs_per_s(1, threads)
+    threads = pick_cpu_threads()                          # fastest thread count on this host (<= all cores)
     t0 = time.perf_counter()
     rate, secs = oracle_pairs_per_s(max(args.steps, 1), threads)    # one frame-pair per "step"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "frame-pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config_dict(1, 1), note="CPU: one frame-pair per step (bounded sample of the same workload)"),
-            "cpu_baseline": {"value": rate, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
                              "sample": f"{max(args.steps, 1)} frame-pairs of the cfg4 shape, oracle port of the reference "
                                        "PyTorch-CPU forward + HiGHS MILP restatement of ortools_solve (OR-tools absent)"},
             "e2e": {"value": rate, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -130,8 +153,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("MMMOT_BENCH_PAIRS", "128")),
                     help="frame-pairs per GPU per step")
-    ap.add_argument("--cpu-pairs", type=int, default=3, help="frame-pairs timed for cpu_baseline (rank 0)")
+    ap.add_argument("--cpu-pairs", type=int, default=2, help="frame-pairs timed for cpu_baseline (rank 0)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tcgen05"],
+                    help="contraction engine (A/B runs; default auto = tcgen05 for this workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -151,6 +176,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    mmmot_b200.set_engine(args.engine)
 
     n, pts, hw = CFG["n"], CFG["pts"], CFG["hw"]
     L, B = 2 * n, args.pairs
@@ -240,24 +266,38 @@ def main():
         conv_ms, conv_flop, conv_n = hook
         achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        roofline = {"bound": "tensor", "kernel": "gemm_simt_kernel<XM_CONV3> (VGG 3x3 conv contraction, FP32 FFMA)",
+        tc_engine = args.engine != "fp32"
+        traffic = None
+        try:    # dram bytes per frame-pair of the 12 conv launches, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_conv3s_traffic.json")) as f:
+                tr = json.load(f)
+            if tc_engine:
+                traffic = tr["dram_bytes_per_pair"] * (B / max(conv_n / (12 * args.steps), 1)) / 12
+        except Exception:
+            pass
+        roofline = {"bound": "tensor",
+                    "kernel": ("tc::gemm_tc_kernel<XM_CONV3S> (tcgen05 3x3-conv contraction of the VGG trunk, FP16 hi/lo "
+                               "split: 3 MMAs per algorithmic MAC)") if tc_engine else
+                              "gemm_simt_kernel<XM_CONV3> (VGG 3x3 conv contraction, FP32 FFMA engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step); the kernel itself issues "
-                                   "FP32 FFMA, whose own ceiling is ~72 TFLOP/s at 1.9 GHz",
+                    "mma_issue_tflops": 3 * achieved if tc_engine else None,
+                    "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step); 'achieved' counts "
+                                   "ALGORITHMIC FLOPs (2*Cout*9Cin*pixels per launch); the tensor pipe executes 3x that",
                     "launches_timed": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
-                    "share_of_step": conv_ms / ms, "traffic": None}
+                    "share_of_step": conv_ms / ms, "traffic": traffic,
+                    "traffic_note": "avg dram bytes per launch, scaled from profiles/r01_conv3s_traffic.json"}
         cpu = None
         if not args.no_cpu:
-            threads = os.cpu_count() or 1
+            threads = pick_cpu_threads()
             rate, secs = oracle_pairs_per_s(args.cpu_pairs, threads)
-            cpu = {"value": rate, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
+            cpu = {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
                    "sample": f"{args.cpu_pairs} frame-pairs of the same cfg4 workload ({secs:.1f} s), oracle port of the reference "
                              "PyTorch-CPU forward + HiGHS restatement of the LP"}
         h2d = h_crops.numel() * 4 + h_points.numel() * 4 + split.numel() * 4
         d2h = h_match.numel() * 4 + h_flags.numel() * 4
         line = {"metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(B, world),
+                "vs_baseline": None, "dtype": "f32 (tcgen05 engine: FP16 hi/lo split operands, fp32 accumulate)" if args.engine != "fp32" else "f32", "data": "synthetic", "config": dict(config_dict(B, world), engine=args.engine),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},

@@ -251,7 +251,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       p.num_tiles = p.tiles_per_group;
       const uint4* wp = (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i];
       const float wsc = wts->tc_scale[MMMOT_W_VGG_WP0 + i];
-      const bool timed = mm_timing_on();
+      const bool timed = mm_timing_on() && i > 0;   // roofline hook: the tcgen05 conv launches only
       if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
       if (i == 0) {
         conv0_packed_kernel<<<mm_cdiv(p.S / 4, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
