@@ -186,6 +186,14 @@ int mmmot_set_debug(int flags);
 int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const float* bias, const float* X,
                        float* Y, int M, int K, int S, int engine, void* stream);
 
+/* Test hooks of the TMA-fed tcgen05 engine: operands are two FP16 planes (hi, lo), channels-last.
+ * linear: Y[rows][M] fp32 = X W^T + bias, X planes [2][rows][K].  conv: 3x3 pad 1 + bias + ReLU on NHWC planes
+ * [2][n][H][W][C] -> [2][n][H][W][M] (weights packed with K order (ky*3+kx)*C + ci). */
+int mmmot_debug_linear_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, float* Y,
+                              int M, int K, long rows, void* stream);
+int mmmot_debug_conv_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, void* Yhi,
+                            int n_img, int H, int W, int C, int M, void* stream);
+
 /* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
  * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed
  * duration (ms), the summed algorithmic FLOPs (2*Cout*9Cin*pixels) and the launch count of every

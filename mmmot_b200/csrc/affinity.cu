@@ -197,7 +197,7 @@ __global__ void softmax_apply_kernel(const float* __restrict__ z, int mode, int 
 
 struct AfWs {
   float *y01, *y2, *y3, *z;
-  uint32_t* xp;   // tensor-core path: packed FP16 (hi|lo) operands [G*NM][512]
+  __half* xp;     // tensor-core path: FP16 hi/lo operand planes [2][G*NM][512]
   float* fcl;     // tensor-core path: channels-last copy of the feature stacks [G][L][512]
   float *sc1, *sh1, *sc0, *sh0, *sc2, *sh2, *sc3, *sh3;
   float *v, *h1, *h2, *nsc1, *nsh1, *nsc2, *nsh2;
@@ -214,7 +214,7 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.y2 = a.take<float>(G * 512 * NM);
   w.y3 = a.take<float>(G * 128 * NM);
   w.z = a.take<float>(G * NM);
-  w.xp = a.take<uint32_t>(G * NM * 512);
+  w.xp = a.take<__half>(2 * G * NM * 512);
   w.fcl = a.take<float>(G * (n + m) * 512);
   w.sc1 = a.take<float>(G * 512); w.sh1 = a.take<float>(G * 512);
   w.sc0 = a.take<float>(G * 512); w.sh0 = a.take<float>(G * 512);
@@ -275,10 +275,11 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
     GemmP p = gemm_defaults();
     p.bias = W[MMMOT_W_AF_B01]; p.M = 1024; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
-    p.X = (const float*)w.xp; p.Cin = 512; p.x_gs = NM;
+    p.x_gs = NM;
     p.Y = w.y01; p.y_gs = NM; p.y_ms = 1024;
     p.part = w.part;
-    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W01P], wts->tc_scale[MMMOT_W_AF_W01P], st, tc::OUT_CL));
+    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W01P], wts->tc_scale[MMMOT_W_AF_W01P], w.xp, rows * 512,
+                               rows, 512, tc::OUT_CL, 0, st));
   } else {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
@@ -337,20 +338,22 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   if (use_tc) {
     // GroupNorm+ReLU applied once per element by norm_split -> packed FP16 operand of the next contraction
     const long rows = (long)G * NM;
-    MM_TRY(norm_split(w.y01, 1024, w.sc1, w.sh1, 512, rows, NM, nullptr, 0, w.xp, 512, st));
+    MM_TRY(norm_split(w.y01, 1024, w.sc1, w.sh1, 512, rows, NM, nullptr, 0, w.xp, st));
     GemmP p = gemm_defaults();
     p.bias = W[MMMOT_W_AF_B2]; p.M = 512; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
-    p.X = (const float*)w.xp; p.Cin = 512; p.x_gs = NM;
+    p.x_gs = NM;
     p.Y = w.y2; p.y_gs = NM; p.y_ms = 512;
     p.part = w.part;
-    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W2P], wts->tc_scale[MMMOT_W_AF_W2P], st, tc::OUT_CL));
+    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W2P], wts->tc_scale[MMMOT_W_AF_W2P], w.xp, rows * 512, rows,
+                               512, tc::OUT_CL, 0, st));
     MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st, 2));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
-    MM_TRY(norm_split(w.y2, 512, w.sc2, w.sh2, 512, rows, NM, nullptr, 0, w.xp, 512, st));
+    MM_TRY(norm_split(w.y2, 512, w.sc2, w.sh2, 512, rows, NM, nullptr, 0, w.xp, st));
     p.bias = W[MMMOT_W_AF_B3]; p.M = 128;
     p.Y = w.y3; p.y_ms = 128;
-    MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)W[MMMOT_W_AF_W3P], wts->tc_scale[MMMOT_W_AF_W3P], st, tc::OUT_CL));
+    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W3P], wts->tc_scale[MMMOT_W_AF_W3P], w.xp, rows * 512, rows,
+                               512, tc::OUT_CL, 0, st));
     MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st, 2));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   } else {

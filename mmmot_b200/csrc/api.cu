@@ -111,3 +111,29 @@ extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scal
   p.tiles_per_group = mm_cdiv(S, 128); p.num_tiles = p.tiles_per_group;
   return gemm_simt_launch<XM_DIRECT>(p, st);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Test hooks for the TMA-fed tcgen05 engine (planar FP16 hi/lo channels-last operands).
+#include "gemm_tma.cuh"
+
+// Y[rows][M] fp32 (channels-last) = X W^T + bias ; X given as planes Xhi[rows][K], Xlo = Xhi + rows*K
+extern "C" int mmmot_debug_linear_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi,
+                                         float* Y, int M, int K, long rows, void* stream) {
+  if (!Wp || !Xhi || !Y || M <= 0 || K <= 0 || rows <= 0) return MMMOT_E_ARG;
+  GemmP p = gemm_defaults();
+  p.bias = bias; p.M = M; p.K = K;
+  p.S = (int)rows; p.tiles_per_group = mm_cdiv(rows, tc::BN); p.num_tiles = p.tiles_per_group;
+  p.Y = Y; p.y_ms = M;
+  return gemm_tma_launch_mat(p, (const uint4*)Wp, wp_scale, (const __half*)Xhi, rows * (long)K, rows, K, tc::OUT_CL, 0,
+                             (cudaStream_t)stream);
+}
+
+// 3x3 conv + bias + ReLU on planar FP16 NHWC: X planes [2][n][H][W][C] -> Y planes [2][n][H][W][M]
+extern "C" int mmmot_debug_conv_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, void* Yhi,
+                                       int n_img, int H, int W, int C, int M, void* stream) {
+  if (!Wp || !Xhi || !Yhi) return MMMOT_E_ARG;
+  GemmP p = gemm_defaults();
+  p.bias = bias; p.M = M; p.relu = 1;
+  return gemm_tma_launch_conv(p, (const uint4*)Wp, wp_scale, (const __half*)Xhi, (long)n_img * H * W * C, n_img, H, W, C,
+                              (__half*)Yhi, (long)n_img * H * W * M, (cudaStream_t)stream);
+}

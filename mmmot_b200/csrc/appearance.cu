@@ -2,7 +2,7 @@
 // Replaces reference modules/appear_net.py:166-190 (vgg_forward + SkipPool.forward :27-32).
 #include <cuda_fp16.h>
 
-#include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace {
 
@@ -44,54 +44,65 @@ __global__ void plane_mean_kernel(const float* __restrict__ in, float* __restric
   if (lane == 0) out[w] = s / (float)hw;
 }
 
-// ---- packed FP16 (hi | lo << 16) NHWC activations of the tensor-core trunk ----
-__device__ __forceinline__ float unpack_split(uint32_t w) {
-  return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))) +
-         __half2float(__ushort_as_half((unsigned short)(w >> 16)));
-}
-
-// 2x2 / stride 2 max-pool on packed NHWC words: the max IS one of the four inputs, so its word is kept.
-__global__ void maxpool2_packed_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long n_out,
-                                       int Ho, int Wo, int C) {
+// ---- FP16 hi/lo planes, NHWC: activations of the tensor-core trunk ([2][n][H][W][C]) ----
+// 2x2 / stride 2 max-pool, 8 channels per thread (128-bit loads).  The max IS one of the four inputs, so its
+// (hi, lo) pair is copied, not re-split.
+__global__ void maxpool2_planar_kernel(const __half* __restrict__ in, __half* __restrict__ out, long n_out8,
+                                       int Ho, int Wo, int C, long plane_in, long plane_out) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_out) return;
-  int c = (int)(idx % C);
-  long t = idx / C;
-  int xo = (int)(t % Wo);
+  if (idx >= n_out8) return;
+  const int c8n = C >> 3;
+  const int c = (int)(idx % c8n) * 8;
+  long t = idx / c8n;
+  const int xo = (int)(t % Wo);
   t /= Wo;
-  int yo = (int)(t % Ho);
-  long img = t / Ho;
+  const int yo = (int)(t % Ho);
+  const long img = t / Ho;
   const long rs = (long)2 * Wo * C;
-  const uint32_t* src = in + ((img * 2 * Ho + 2 * yo) * 2 * Wo + 2 * xo) * (long)C + c;
-  uint32_t w = src[0], w1 = src[C], w2 = src[rs], w3 = src[rs + C];
-  float m = unpack_split(w), f;
-  f = unpack_split(w1); if (f > m) { m = f; w = w1; }
-  f = unpack_split(w2); if (f > m) { m = f; w = w2; }
-  f = unpack_split(w3); if (f > m) { m = f; w = w3; }
-  out[idx] = w;
+  const __half* src = in + ((img * 2 * Ho + 2 * yo) * 2 * Wo + 2 * xo) * (long)C + c;
+  const long offs[4] = {0, (long)C, rs, rs + C};
+  uint4 bh, bl;
+  float best[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint4 h = *reinterpret_cast<const uint4*>(src + offs[k]);
+    const uint4 l = *reinterpret_cast<const uint4*>(src + offs[k] + plane_in);
+    const __half* hh = reinterpret_cast<const __half*>(&h);
+    const __half* ll = reinterpret_cast<const __half*>(&l);
+    __half* oh = reinterpret_cast<__half*>(&bh);
+    __half* ol = reinterpret_cast<__half*>(&bl);
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const float f = __half2float(hh[e]) + __half2float(ll[e]);
+      if (k == 0 || f > best[e]) { best[e] = f; oh[e] = hh[e]; ol[e] = ll[e]; }
+    }
+  }
+  __half* dst = out + ((img * Ho + yo) * (long)Wo + xo) * C + c;
+  *reinterpret_cast<uint4*>(dst) = bh;
+  *reinterpret_cast<uint4*>(dst + plane_out) = bl;
 }
 
-// global average of every (img, channel) over the hw pixels of a packed NHWC map -> pooled[img][C] fp32
-__global__ void plane_mean_packed_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, long n_img,
-                                         int hw, int C) {
+// global average of every (img, channel) over the hw pixels of a planar NHWC map -> pooled[img][C] fp32
+__global__ void plane_mean_planar_kernel(const __half* __restrict__ in, float* __restrict__ out, long n_img,
+                                         int hw, int C, long plane) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_img * C) return;
-  int c = (int)(idx % C);
-  long img = idx / C;
-  const uint32_t* src = in + img * hw * (long)C + c;
+  const int c = (int)(idx % C);
+  const long img = idx / C;
+  const __half* src = in + img * hw * (long)C + c;
   float s = 0.f;
-  for (int i = 0; i < hw; i++) s += unpack_split(src[(long)i * C]);
+  for (int i = 0; i < hw; i++) s += __half2float(src[(long)i * C]) + __half2float(src[(long)i * C + plane]);
   out[idx] = s / (float)hw;
 }
 
 // First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound:
-// 1 MB of output per crop), so a direct FP32 FFMA kernel writes the packed FP16 (hi|lo) NHWC words the next
-// layer's operand producers expect.  Each thread: 4 consecutive pixels x 16 channels (weights read from smem
+// 1 MB of output per crop), so a direct FP32 FFMA kernel writes the FP16 hi/lo NHWC planes the next layer's
+// TMA loads read.  Each thread: 4 consecutive pixels x 16 channels (weights read from smem
 // once per 4 pixels as 128-bit loads); CTA = 64 pixel quads x 4 channel groups.  wt: [(ky*3+kx)*3 + ci][64]
 // (BN folded), ReLU fused.  W % 4 == 0.
 __global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, long n_quads, int H, int W,
-                                                           uint32_t* __restrict__ out) {
+                                                           __half* __restrict__ out, long plane) {
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
@@ -140,16 +151,14 @@ __global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restri
   const long pix0 = row * W + x0;
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    uint4* dst = reinterpret_cast<uint4*>(out + (pix0 + p) * 64 + cg);
+    __half h[16], l[16];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      uint4 o;
-      o.x = tc::pack_split_f16(fmaxf(acc[p][4 * q], 0.f));
-      o.y = tc::pack_split_f16(fmaxf(acc[p][4 * q + 1], 0.f));
-      o.z = tc::pack_split_f16(fmaxf(acc[p][4 * q + 2], 0.f));
-      o.w = tc::pack_split_f16(fmaxf(acc[p][4 * q + 3], 0.f));
-      dst[q] = o;
-    }
+    for (int c = 0; c < 16; c++) tma::split_f16(fmaxf(acc[p][c], 0.f), h[c], l[c]);
+    __half* dst = out + (pix0 + p) * 64 + cg;
+    reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
+    reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
+    reinterpret_cast<uint4*>(dst + plane)[0] = reinterpret_cast<uint4*>(l)[0];
+    reinterpret_cast<uint4*>(dst + plane)[1] = reinterpret_cast<uint4*>(l)[1];
   }
 }
 
@@ -230,49 +239,45 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
   for (int s = 0; s < 4; s++) pooled[s] = ar.take<float>((size_t)n_img * kSkipC[s]);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
 
-  // Tensor-core trunk: activations live as packed FP16 (hi|lo) NHWC words between layers; the
-  // epilogue of one conv writes exactly what the next conv's operand producers consume.
+  // Tensor-core trunk: activations live as FP16 hi/lo NHWC planes between layers; the epilogue of one conv
+  // writes exactly what the next conv's TMA loads read (3x3 taps = shifted boxes, padding = TMA zero fill).
   const bool tc_trunk = mm_engine() == 2 || (mm_engine() == 0 && (long)n_img * H * W >= 65536);
   if (tc_trunk) {
-    const void* cur = crops;
+    __half* hb[2] = {reinterpret_cast<__half*>(buf[0]), reinterpret_cast<__half*>(buf[1])};
+    const __half* cur = nullptr;
+    long cur_plane = 0;
     int which = 0, h = H, w = W;
     for (int i = 0; i < 13; i++) {
-      GemmP p = gemm_defaults();
-      p.bias = wts->w[MMMOT_W_VGG_B0 + i];
-      p.M = kVggCout[i];
-      p.K = 9 * kVggCin[i];
-      p.Cin = kVggCin[i];
-      p.H = h; p.W = w;
-      p.S = n_img * h * w;
-      p.X = (const float*)cur;
-      p.Y = buf[which]; p.y_ms = p.M;
-      p.relu = 1;
-      p.tiles_per_group = mm_cdiv(p.S, tc::BN);
-      p.num_tiles = p.tiles_per_group;
-      const uint4* wp = (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i];
-      const float wsc = wts->tc_scale[MMMOT_W_VGG_WP0 + i];
-      const bool timed = mm_timing_on() && i > 0;   // roofline hook: the tcgen05 conv launches only
-      if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
+      const int cout = kVggCout[i], cin = kVggCin[i];
+      const long plane_out = (long)n_img * h * w * cout;
       if (i == 0) {
-        conv0_packed_kernel<<<mm_cdiv(p.S / 4, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
-                                                                 (long)p.S / 4, h, w, (uint32_t*)buf[which]);
+        const long quads = (long)n_img * h * w / 4;
+        conv0_packed_kernel<<<mm_cdiv(quads, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0], quads,
+                                                               h, w, hb[which], plane_out);
         MM_LAUNCH_CHECK();
       } else {
-        MM_TRY(gemm_tc_launch<XM_CONV3S>(p, wp, wsc, st, tc::OUT_PACKED));
+        GemmP p = gemm_defaults();
+        p.bias = wts->w[MMMOT_W_VGG_B0 + i];
+        p.M = cout;
+        p.relu = 1;
+        const bool timed = mm_timing_on();   // roofline hook: the tcgen05 conv launches
+        if (timed) mm_timing_begin(st, 2.0 * cout * 9.0 * cin * (double)n_img * h * w);
+        MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
+                                    cur_plane, n_img, h, w, cin, hb[which], plane_out, st));
+        if (timed) mm_timing_end(st);
       }
-      if (timed) mm_timing_end(st);
-      cur = buf[which]; which ^= 1;
+      cur = hb[which]; cur_plane = plane_out; which ^= 1;
       if (kPoolAfter[i]) {
         h /= 2; w /= 2;
-        long n_out = (long)n_img * kVggCout[i] * h * w;
-        maxpool2_packed_kernel<<<mm_cdiv(n_out, 256), 256, 0, st>>>((const uint32_t*)cur, (uint32_t*)buf[which], n_out,
-                                                                   h, w, kVggCout[i]);
+        const long plane_p = (long)n_img * h * w * cout;
+        const long n8 = plane_p / 8;
+        maxpool2_planar_kernel<<<mm_cdiv(n8, 256), 256, 0, st>>>(cur, hb[which], n8, h, w, cout, cur_plane, plane_p);
         MM_LAUNCH_CHECK();
-        cur = buf[which]; which ^= 1;
+        cur = hb[which]; cur_plane = plane_p; which ^= 1;
         int s = kSkipAfter[i];
         if (s >= 0) {
-          plane_mean_packed_kernel<<<mm_cdiv((long)n_img * kSkipC[s], 128), 128, 0, st>>>(
-              (const uint32_t*)cur, pooled[s], n_img, h * w, kSkipC[s]);
+          plane_mean_planar_kernel<<<mm_cdiv((long)n_img * kSkipC[s], 128), 128, 0, st>>>(cur, pooled[s], n_img, h * w,
+                                                                                         kSkipC[s], cur_plane);
           MM_LAUNCH_CHECK();
         }
       }

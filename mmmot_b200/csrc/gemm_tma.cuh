@@ -1,0 +1,417 @@
+// tcgen05 contraction engine, TMA-fed variant (sm_100a).
+//
+// Same arithmetic as gemm_tc.cuh (FP16 hi/lo split operands, 3 MMAs per k-step, FP32 accumulate in
+// TMEM, fused epilogue) but the generated operand is not produced by threads: activations between
+// tensor-core layers live in HBM as two FP16 planes (hi, lo), channels-last, and the TMA engine
+// (cp.async.bulk.tensor, tiled mode, 64-byte swizzle) drops each [256 rows x 32 channels] box straight
+// into shared memory in the UMMA K-major SWIZZLE_64B layout:
+//   * 1x1 contraction: 2-D map [rows][C], box (32, 256)
+//   * 3x3 convolution: 4-D map [img][H][W][C], box (32, bx, by, bi) with bx*by*bi = 256; the 9 taps are the
+//     same box at shifted (x, y) coordinates and the zero padding is TMA's out-of-bounds fill — no im2col,
+//     no boundary code, no index arithmetic on the SMs.
+// CTA (320 threads, persistent, one per SM): warps 0-7 epilogue (two per TMEM lane quadrant, one per
+// column half), warp 8 MMA issuer, warp 9 loader (weights by cp.async.bulk, operand boxes by TMA).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "gemm_tc.cuh"
+
+namespace tma {
+
+using namespace tc;
+
+constexpr int T_THREADS = 320;
+constexpr int T_EPI_WARPS = 8, T_MMA_WARP = 8, T_LOAD_WARP = 9;
+constexpr int T_SCRATCH = 0;
+constexpr size_t T_SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+
+enum { OUT_PLANAR = 3 };   // two FP16 planes Y_hi[row][y_ms], Y_lo = Y_hi + plane_elems (channels-last)
+
+struct TmaP {
+  TcP t;                    // .g: M, K, bias, relu, part, Y, y_ms, y_gs, S/tiles ...
+  int conv;                 // 0: rows x C matrix ; 1: 3x3 conv on [img][H][W][C]
+  int bx, by, bi;           // conv box (pixels): columns of a tile = (ii*by + yy)*bx + xx
+  int tiles_x, tiles_y;     // conv tile grid per image group
+  int n_img, H, W, C;       // conv geometry (C = input channels)
+  long plane_elems;         // output: distance (in fp16 elements) between the hi and lo planes
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mbar)
+      : "memory");
+}
+// K-major SWIZZLE_64B operand: rows of 64 bytes (32 fp16), 8-row groups 512 B apart (SBO), layout type 4.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  unsigned short a, b;
+  asm("{\n\t.reg .f32 f;\n\t"
+      "cvt.rn.satfinite.f16.f32 %0, %2;\n\t"
+      "cvt.f32.f16 f, %0;\n\t"
+      "sub.f32 f, %2, f;\n\t"
+      "cvt.rn.satfinite.f16.f32 %1, f;\n\t}"
+      : "=h"(a), "=h"(b)
+      : "f"(x));
+  hi = __ushort_as_half(a);
+  lo = __ushort_as_half(b);
+}
+
+static __global__ void __launch_bounds__(T_THREADS, 1)
+gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  const GemmP& p = P.t.g;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES), tempty_bar = bar0 + 8u * (2 * STAGES + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = P.t.mt_per_cta;
+  const int mgroups = (P.t.m_tiles + MT - 1) / MT;
+  const long total_tiles = (long)p.num_tiles * mgroups;
+  // K chunks: conv = 9 taps x (C / 32) channel chunks, K order k = tap*C + ci ; matrix = K / 32
+  const int KC = P.t.k_chunks;
+  const int cchunks = P.conv ? P.C / BK : KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar(s), 1);   // the loader's single expect_tx arrive (weights + 2 operand boxes)
+      mbar_init(empty_bar(s), 1);  // tcgen05.commit
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, T_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == T_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (m group, column tile) ; column tile -> group / first column (matrix) or box origin (conv)
+  auto tile_cols = [&](int nt, int& g, int& c0, int& len) {
+    if (p.tile_tab) { int4 tt = p.tile_tab[nt]; g = tt.x; c0 = tt.y; len = tt.z; }
+    else { g = nt / p.tiles_per_group; c0 = (nt - g * p.tiles_per_group) * BN; len = min(BN, p.S - c0); }
+  };
+  auto conv_origin = [&](int nt, int& i0, int& y0, int& x0) {
+    const int tx = nt % P.tiles_x;
+    const int r = nt / P.tiles_x;
+    const int ty = r % P.tiles_y;
+    i0 = (r / P.tiles_y) * P.bi; y0 = ty * P.by; x0 = tx * P.bx;
+  };
+
+  if (warp < T_EPI_WARPS) {
+    // =============================== EPILOGUE ===============================
+    const int q = warp & 3, half = warp >> 2;
+    uint32_t tphase = 0;
+    __half* yh = reinterpret_cast<__half*>(p.Y);
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mg = (int)(t % mgroups);
+      const int nt = (int)(t / mgroups);
+      int g = 0, c0 = 0, len = BN, i0 = 0, y0 = 0, x0 = 0;
+      if (P.conv) conv_origin(nt, i0, y0, x0); else tile_cols(nt, g, c0, len);
+      mbar_wait(tfull_bar, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+      for (int mt = 0; mt < MT; mt++) {
+        const int co = (mg * MT + mt) * 128 + q * 32 + lane;
+        const bool rowok = co < p.M;
+        const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
+        double d1 = 0.0, d2 = 0.0;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; cc++) {
+          const int col0 = half * 128 + cc * 32;
+          if (col0 >= len) break;   // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
+          if (P.t.dbg & 1) continue;
+          float s1 = 0.f, s2 = 0.f;
+          bool fast = col0 + 32 <= len;
+          float bva = bv;
+          if (fast && p.addend) {
+            const int da = __ldg(p.seg + c0 + col0), db = __ldg(p.seg + c0 + col0 + 31);
+            if (da == db) { if (rowok) bva += __ldg(p.addend + (long)da * p.ld_add + co); }
+            else fast = false;
+          }
+          if (fast) {
+            if (p.relu) epi_fast<true>(v, P.t.out_scale, bva, s1, s2);
+            else epi_fast<false>(v, P.t.out_scale, bva, s1, s2);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float x = fmaf(__uint_as_float(v[j]), P.t.out_scale, bv);
+              const int col = col0 + j;
+              if (p.addend && rowok && col < len)
+                x += __ldg(p.addend + (long)__ldg(p.seg + c0 + col) * p.ld_add + co);
+              if (p.relu) x = fmaxf(x, 0.f);
+              v[j] = __float_as_uint(x);
+              if (col < len) { s1 += x; s2 = fmaf(x, x, s2); }
+            }
+          }
+          d1 += (double)s1; d2 += (double)s2;
+          if (!p.Y || !rowok) continue;
+          if (P.conv) {
+            // column -> pixel of the box; planar FP16 (hi, lo) NHWC output
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int col = col0 + j;
+              const int xx = col % P.bx, r = col / P.bx;
+              const int yy = r % P.by, ii = r / P.by;
+              const int img = i0 + ii, y = y0 + yy, x = x0 + xx;
+              if (img < P.n_img && y < P.H && x < P.W) {
+                const long o = (((long)img * P.H + y) * P.W + x) * p.y_ms + co;
+                __half h, l;
+                split_f16(__uint_as_float(v[j]), h, l);
+                yh[o] = h;
+                yh[o + P.plane_elems] = l;
+              }
+            }
+          } else {
+            const int nvalid = min(32, len - col0);
+            const long row0 = (long)g * p.y_gs + c0 + col0;
+            if (P.t.out_mode == OUT_PLANAR) {
+              __half* dst = yh + row0 * p.y_ms + co;
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < nvalid) {
+                  __half h, l;
+                  split_f16(__uint_as_float(v[j]), h, l);
+                  dst[(long)j * p.y_ms] = h;
+                  dst[(long)j * p.y_ms + P.plane_elems] = l;
+                }
+            } else {   // OUT_CL fp32 channels-last
+              float* dst = p.Y + row0 * p.y_ms + co;
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (j < nvalid) dst[(long)j * p.y_ms] = __uint_as_float(v[j]);
+            }
+          }
+        }
+        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2(d1, d2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+  } else if (warp == T_MMA_WARP) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, tcount++) {
+        mbar_wait(tempty_bar, (tcount & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < KC; kc++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_SUB;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            if (mt < MT && !(P.t.dbg & 8)) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++) {
+                const uint64_t a_hi = smem_desc(sa + mt * A_SUB + ks * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t a_lo = smem_desc(sa + mt * A_SUB + A_HALF + ks * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t b_hi = smem_desc_sw64(sb + ks * 32);
+                const uint64_t b_lo = smem_desc_sw64(sb + B_HALF + ks * 32);
+                const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+                umma_f16(d, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
+                umma_f16(d, a_hi, b_lo, IDESC, 1u);
+                umma_f16(d, a_lo, b_hi, IDESC, 1u);
+              }
+            }
+          }
+          umma_commit(empty_bar(s));
+          if (kc == KC - 1) umma_commit(tfull_bar);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== LOADER (weights + operand boxes) ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mg = (int)(t % mgroups);
+        const int nt = (int)(t / mgroups);
+        const int mt0 = mg * MT;
+        const int nmt = min(MT, P.t.m_tiles - mt0);
+        int g = 0, c0 = 0, len = BN, i0 = 0, y0 = 0, x0 = 0;
+        if (P.conv) conv_origin(nt, i0, y0, x0); else tile_cols(nt, g, c0, len);
+        const int row0 = (int)((long)g * p.x_gs + c0);
+        for (int kc = 0; kc < KC; kc++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          const uint32_t abytes = (uint32_t)nmt * A_SUB;
+          mbar_expect_tx(full_bar(s), abytes + 2 * B_HALF);
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_SUB;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t.Wp) + ((size_t)kc * P.t.m_tiles + mt0) * A_SUB;
+          bulk_g2s(sa, src, abytes, full_bar(s));
+          if (P.conv) {
+            const int tap = kc / cchunks, cc = kc - tap * cchunks;
+            const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+            tma_load_4d(sb, &map_hi, cc * BK, x0 + dx, y0 + dy, i0, full_bar(s));
+            tma_load_4d(sb + B_HALF, &map_lo, cc * BK, x0 + dx, y0 + dy, i0, full_bar(s));
+          } else {
+            tma_load_2d(sb, &map_hi, kc * BK, row0, full_bar(s));
+            tma_load_2d(sb + B_HALF, &map_lo, kc * BK, row0, full_bar(s));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no libcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// fp16 [rows][C] matrix (row stride ld elements), box 32 x 256, 64-byte swizzle
+static inline int make_map_2d(CUtensorMap* m, const void* basep, long rows, int C, long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MMMOT_E_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 256}, es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(basep), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+}
+// fp16 NHWC [n_img][H][W][C], box (32, bx, by, bi)
+static inline int make_map_4d(CUtensorMap* m, const void* basep, int n_img, int H, int W, int C, int bx, int by,
+                              int bi) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return MMMOT_E_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bi}, es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(basep), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+}
+
+}  // namespace tma
+
+// 1x1 contraction on planar FP16 (hi, lo) channels-last activations X_hi[rows][ldx], X_lo = X_hi + x_plane.
+// g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
+static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
+                               long rows, int ldx, int out_mode, long y_plane, cudaStream_t st) {
+  if (!Wp || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    MM_CUDA(cudaGetDevice(&dev));
+    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tma::T_SMEM_BYTES));
+  }
+  tma::TmaP P;
+  memset(&P, 0, sizeof(P));
+  P.t.g = g;
+  P.t.Wp = Wp;
+  P.t.m_tiles = (g.M + 127) / 128;
+  P.t.k_chunks = g.K / tc::BK;
+  P.t.mt_per_cta = P.t.m_tiles >= 2 ? 2 : 1;
+  P.t.out_scale = out_scale;
+  P.t.out_mode = out_mode;
+  P.t.dbg = mm_debug_flags();
+  P.plane_elems = y_plane;
+  alignas(64) CUtensorMap mh, ml;
+  MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
+  MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));
+  const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
+  const long total = (long)g.num_tiles * mgroups;
+  const int grid = (int)(total < sms ? total : sms);
+  tma::gemm_tma_kernel<<<grid, tma::T_THREADS, tma::T_SMEM_BYTES, st>>>(P, mh, ml);
+  MM_LAUNCH_CHECK();
+  return 0;
+}
+
+// 3x3 / pad 1 convolution on planar FP16 NHWC activations; output planar FP16 NHWC (ReLU via g.relu).
+static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
+                                int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st) {
+  if (!Wp || C % tc::BK) return MMMOT_E_ARG;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    MM_CUDA(cudaGetDevice(&dev));
+    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tma::T_SMEM_BYTES));
+  }
+  // box of 256 pixels: as wide as the image allows (power of two), then rows, then images
+  int bx = 1; while (bx * 2 <= W && bx * 2 <= 256) bx *= 2;
+  int by = 1; while (by * 2 <= H && bx * by * 2 <= 256) by *= 2;
+  const int bi = 256 / (bx * by);
+  tma::TmaP P;
+  memset(&P, 0, sizeof(P));
+  GemmP g = g0;
+  g.K = 9 * C;
+  P.conv = 1; P.bx = bx; P.by = by; P.bi = bi;
+  P.tiles_x = mm_cdiv(W, bx); P.tiles_y = mm_cdiv(H, by);
+  P.n_img = n_img; P.H = H; P.W = W; P.C = C;
+  g.num_tiles = P.tiles_x * P.tiles_y * mm_cdiv(n_img, bi);
+  g.tile_tab = nullptr;
+  g.Y = reinterpret_cast<float*>(Yhi);
+  g.y_ms = g.M;
+  P.t.g = g;
+  P.t.Wp = Wp;
+  P.t.m_tiles = (g.M + 127) / 128;
+  P.t.k_chunks = g.K / tc::BK;
+  P.t.mt_per_cta = P.t.m_tiles >= 2 ? 2 : 1;
+  P.t.out_scale = out_scale;
+  P.t.out_mode = tma::OUT_PLANAR;
+  P.t.dbg = mm_debug_flags();
+  P.plane_elems = y_plane;
+  alignas(64) CUtensorMap mh, ml;
+  MM_TRY(tma::make_map_4d(&mh, Xhi, n_img, H, W, C, bx, by, bi));
+  MM_TRY(tma::make_map_4d(&ml, Xhi + x_plane, n_img, H, W, C, bx, by, bi));
+  const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
+  const long total = (long)g.num_tiles * mgroups;
+  const int grid = (int)(total < sms ? total : sms);
+  tma::gemm_tma_kernel<<<grid, tma::T_THREADS, tma::T_SMEM_BYTES, st>>>(P, mh, ml);
+  MM_LAUNCH_CHECK();
+  return 0;
+}

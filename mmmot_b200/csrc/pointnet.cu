@@ -83,7 +83,7 @@ __global__ void segment_mean_cl_kernel(const float* __restrict__ Y, int C, const
 
 struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *ut, *hmean, *o;
-  uint32_t *x1p, *xp;   // tensor-core path: packed FP16 (hi|lo) normalised activations [P][64], [P][128]
+  __half *x1p, *xp;     // tensor-core path: FP16 hi/lo planes of normalised activations [2][P][64], [2][P][128]
   float *sc1, *sh1, *sc, *sh;
   double* stats;
   double2* part;
@@ -99,8 +99,8 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
   w.t0 = a.take<float>(128 * P);
   w.t1 = a.take<float>(64 * P);
   w.big = a.take<float>(1024 * P);
-  w.x1p = a.take<uint32_t>(64 * P);
-  w.xp = a.take<uint32_t>(128 * P);
+  w.x1p = a.take<__half>(2 * 64 * P);
+  w.xp = a.take<__half>(2 * 128 * P);
   w.gmean = a.take<float>(1024 * nd);
   w.u = a.take<float>(512 * nd);
   w.ut = a.take<float>(512 * nd);
@@ -182,14 +182,13 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       if (i == 0) {
         p.X = w.xt; p.x_ks = P;                                 // fp32 [3][P] gather
         MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st, tc::OUT_CL));
-      } else {
-        p.X = (const float*)(i == 1 ? w.x1p : w.xp); p.Cin = cin[i];   // packed [P][cin]
-        MM_TRY(gemm_tc_launch<XM_PACKED>(p, wp, wps, st, tc::OUT_CL));
+      } else {                                                  // FP16 hi/lo planes [2][P][cin] via TMA
+        MM_TRY(gemm_tma_launch_mat(p, wp, wps, i == 1 ? w.x1p : w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st));
       }
       MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
       if (i < 4)
-        MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, cout[i], st));
+        MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, st));
     }
     segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 1024, det_split, w.sc, w.sh, ndet, L, w.gmean);
     MM_LAUNCH_CHECK();
@@ -206,12 +205,11 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       GemmP p = gemm_defaults();
       p.bias = wts->w[MMMOT_W_PN_BH]; p.M = 512; p.K = 64;
       p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
-      p.X = (const float*)w.x1p; p.Cin = 64;
       p.Y = w.big; p.y_ms = 512;
       p.part = w.part;
       p.addend = w.ut; p.seg = w.seg; p.ld_add = 512;
-      MM_TRY(gemm_tc_launch<XM_PACKED>(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], st,
-                                       tc::OUT_CL));
+      MM_TRY(gemm_tma_launch_mat(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], w.x1p, P * 64, P,
+                                 64, tc::OUT_CL, 0, st));
       MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1, w.sc, w.sh, st));
       segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 512, det_split, w.sc, w.sh, ndet, L, w.hmean);

@@ -2,14 +2,22 @@
 // are stored [row][channel], fp32 before the GroupNorm statistics are known and packed FP16 (hi|lo)
 // after normalisation.
 #pragma once
-#include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
-// out[row][c] = split(relu(in[row][c]*sc[g][c] + sh[g][c])),  g = seg ? seg[row] / L : row / rows_per_group.
-// GroupNorm + ReLU of the producer layer applied once per element, emitted as the packed FP16 (hi|lo)
-// words the next contraction's operand producers copy straight into shared memory.
+__device__ __forceinline__ void split4_store(float4 x, __half* hi, __half* lo) {
+  __half h[4], l[4];
+  tma::split_f16(x.x, h[0], l[0]); tma::split_f16(x.y, h[1], l[1]);
+  tma::split_f16(x.z, h[2], l[2]); tma::split_f16(x.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<uint2*>(l);
+}
+
+// out planes [2][rows][C] (hi, lo) = split(relu(in[row][c]*sc[g][c] + sh[g][c])),
+// g = seg ? seg[row] / L : row / rows_per_group.  GroupNorm + ReLU of the producer layer applied once per
+// element and emitted as the FP16 hi/lo planes the next contraction's TMA loads read.
 static __global__ void norm_split_kernel(const float* __restrict__ in, long ldi, const float* __restrict__ sc,
                                          const float* __restrict__ sh, int C, long rows, int rows_per_group,
-                                         const int* __restrict__ seg, int L, uint32_t* __restrict__ out, long ldo) {
+                                         const int* __restrict__ seg, int L, __half* __restrict__ out) {
   const int c4n = C >> 2;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * c4n) return;
@@ -19,18 +27,15 @@ static __global__ void norm_split_kernel(const float* __restrict__ in, long ldi,
   const float4 x = *reinterpret_cast<const float4*>(in + row * ldi + c);
   const float4 a = *reinterpret_cast<const float4*>(sc + (long)g * C + c);
   const float4 b = *reinterpret_cast<const float4*>(sh + (long)g * C + c);
-  uint4 o;
-  o.x = tc::pack_split_f16(fmaxf(fmaf(x.x, a.x, b.x), 0.f));
-  o.y = tc::pack_split_f16(fmaxf(fmaf(x.y, a.y, b.y), 0.f));
-  o.z = tc::pack_split_f16(fmaxf(fmaf(x.z, a.z, b.z), 0.f));
-  o.w = tc::pack_split_f16(fmaxf(fmaf(x.w, a.w, b.w), 0.f));
-  *reinterpret_cast<uint4*>(out + row * ldo + c) = o;
+  float4 y;
+  y.x = fmaxf(fmaf(x.x, a.x, b.x), 0.f); y.y = fmaxf(fmaf(x.y, a.y, b.y), 0.f);
+  y.z = fmaxf(fmaf(x.z, a.z, b.z), 0.f); y.w = fmaxf(fmaf(x.w, a.w, b.w), 0.f);
+  split4_store(y, out + row * C + c, out + rows * C + row * C + c);
 }
 
 static inline int norm_split(const float* in, long ldi, const float* sc, const float* sh, int C, long rows,
-                             int rows_per_group, const int* seg, int L, uint32_t* out, long ldo, cudaStream_t st) {
-  norm_split_kernel<<<mm_cdiv(rows * (C / 4), 256), 256, 0, st>>>(in, ldi, sc, sh, C, rows, rows_per_group, seg, L,
-                                                                  out, ldo);
+                             int rows_per_group, const int* seg, int L, __half* out, cudaStream_t st) {
+  norm_split_kernel<<<mm_cdiv(rows * (C / 4), 256), 256, 0, st>>>(in, ldi, sc, sh, C, rows, rows_per_group, seg, L, out);
   MM_LAUNCH_CHECK();
   return 0;
 }
@@ -60,13 +65,13 @@ static inline int transpose_f32(const float* src, float* dst, int rows, int cols
   return 0;
 }
 
-// Pairwise operand of the affinity contraction (reference modules/gcn.py:6-41) emitted directly as packed
-// FP16 (hi|lo) channels-last words:  x[(g*N + i)*M + j][c] = f[g][i][c] (*|-) f[g][N + j][c], from the
-// channels-last feature stacks fcl[g][L][512].  (fp32 x is never stored; 4 B/element like fp32 but already
-// in the tensor-core operand format.)
+// Pairwise operand of the affinity contraction (reference modules/gcn.py:6-41) emitted directly as FP16 hi/lo
+// planes [2][G*N*M][512]:  x[(g*N + i)*M + j][c] = f[g][i][c] (*|-) f[g][N + j][c], from the channels-last
+// feature stacks fcl[g][L][512].  (fp32 x is never stored; 4 B/element like fp32 but already in the
+// tensor-core operand format.)
 template <int OP>
 static __global__ void pair_split_kernel(const float* __restrict__ fcl, int n, int m, long rows,
-                                         uint32_t* __restrict__ out) {
+                                         __half* __restrict__ out) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * 128) return;
   const long row = idx >> 7;
@@ -83,8 +88,5 @@ static __global__ void pair_split_kernel(const float* __restrict__ fcl, int n, i
     x.x = fabsf((a.x - b.x) * 0.5f); x.y = fabsf((a.y - b.y) * 0.5f);
     x.z = fabsf((a.z - b.z) * 0.5f); x.w = fabsf((a.w - b.w) * 0.5f);
   } else { x.x = (a.x - b.x) * 0.5f; x.y = (a.y - b.y) * 0.5f; x.z = (a.z - b.z) * 0.5f; x.w = (a.w - b.w) * 0.5f; }
-  uint4 o;
-  o.x = tc::pack_split_f16(x.x); o.y = tc::pack_split_f16(x.y);
-  o.z = tc::pack_split_f16(x.z); o.w = tc::pack_split_f16(x.w);
-  *reinterpret_cast<uint4*>(out + row * 512 + c) = o;
+  split4_store(x, out + row * 512 + c, out + rows * 512 + row * 512 + c);
 }
