@@ -155,6 +155,7 @@ def main():
                     help="frame-pairs per GPU per step")
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame-pairs timed for cpu_baseline (rank 0)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kseg", type=int, default=-1, help="tcgen05 conv K-segment length in 32-chunks (0 = off; default: library default)")
     ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tcgen05"],
                     help="contraction engine (A/B runs; default auto = tcgen05 for this workload)")
     args = ap.parse_args()
@@ -177,6 +178,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     mmmot_b200.set_engine(args.engine)
+    if args.kseg >= 0:
+        lib.mmmot_set_kseg(args.kseg)
 
     n, pts, hw = CFG["n"], CFG["pts"], CFG["hw"]
     L, B = 2 * n, args.pairs

@@ -177,6 +177,12 @@ int mmmot_lp_assign(const float* det, long det_stride, const float* link, long l
  * implement the same contraction; the switch exists for A/B parity tests and profiling. */
 int mmmot_set_engine(int engine);
 
+/* Accuracy / speed knob of the tcgen05 conv engine.  The tensor core's fp32 accumulator rounds toward zero at
+ * every K=16 step (bias ~ steps * 2^-25), so K chains longer than `chunks` x 32 are accumulated in several
+ * TMEM passes whose partial sums are added in fp32 round-to-nearest.  0 = single pass (fastest),
+ * 72 (default) splits only the K = 4608 layers, 36 also the K = 2304 layers. */
+int mmmot_set_kseg(int chunks);
+
 /* Profiling experiments on the tcgen05 engine (bit 0 skip epilogue work, 1 skip weight loads, 2 skip
  * operand generation, 3 skip MMA issue); results are WRONG with any bit set.  Default 0. */
 int mmmot_set_debug(int flags);
@@ -192,7 +198,8 @@ int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const fl
 int mmmot_debug_linear_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, float* Y,
                               int M, int K, long rows, void* stream);
 int mmmot_debug_conv_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, void* Yhi,
-                            int n_img, int H, int W, int C, int M, void* stream);
+                            int n_img, int H, int W, int C, int M, float* kseg_scratch /* fp32 [n*H*W][M] or NULL */,
+                            void* stream);
 
 /* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
  * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed

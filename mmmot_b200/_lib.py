@@ -49,9 +49,10 @@ SIGNATURES = {
     "mmmot_launch_count": (ctypes.c_ulonglong, []),
     "mmmot_set_engine": (_i, [_i]),
     "mmmot_set_debug": (_i, [_i]),
+    "mmmot_set_kseg": (_i, [_i]),
     "mmmot_debug_linear": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mmmot_debug_linear_planar": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _l, _vp]),
-    "mmmot_debug_conv_planar": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mmmot_debug_conv_planar": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmmot_timing_enable": (_i, [_i]),
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),

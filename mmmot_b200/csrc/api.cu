@@ -83,7 +83,9 @@ extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* 
 // Engine selection + single-contraction test hook.
 #include "gemm_tc.cuh"
 
-namespace { int g_engine = 0; int g_dbg = 0; }
+namespace { int g_engine = 0; int g_dbg = 0; int g_kseg = 36; }
+int mm_kseg_chunks() { return g_kseg; }
+extern "C" int mmmot_set_kseg(int chunks) { if (chunks < 0) return MMMOT_E_ARG; g_kseg = chunks; return 0; }
 int mm_debug_flags() { return g_dbg; }
 extern "C" int mmmot_set_debug(int flags) { g_dbg = flags; return 0; }
 
@@ -130,10 +132,10 @@ extern "C" int mmmot_debug_linear_planar(const void* Wp, float wp_scale, const f
 
 // 3x3 conv + bias + ReLU on planar FP16 NHWC: X planes [2][n][H][W][C] -> Y planes [2][n][H][W][M]
 extern "C" int mmmot_debug_conv_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi, void* Yhi,
-                                       int n_img, int H, int W, int C, int M, void* stream) {
+                                       int n_img, int H, int W, int C, int M, float* kseg_scratch, void* stream) {
   if (!Wp || !Xhi || !Yhi) return MMMOT_E_ARG;
   GemmP p = gemm_defaults();
   p.bias = bias; p.M = M; p.relu = 1;
   return gemm_tma_launch_conv(p, (const uint4*)Wp, wp_scale, (const __half*)Xhi, (long)n_img * H * W * C, n_img, H, W, C,
-                              (__half*)Yhi, (long)n_img * H * W * M, (cudaStream_t)stream);
+                              (__half*)Yhi, (long)n_img * H * W * M, (cudaStream_t)stream, kseg_scratch);
 }

@@ -223,6 +223,7 @@ extern "C" size_t mmmot_appearance_workspace(int n_img, int H, int W) {
   a.take<float>(act);
   a.take<float>(act);
   for (int s = 0; s < 4; s++) a.take<float>((size_t)n_img * kSkipC[s]);
+  a.take<float>((size_t)(n_img + 16) * H * W * 16);   // K-segment partial sums, tile order (largest: 256 ch at H/4 x W/4)
   return a.off;
 }
 
@@ -237,6 +238,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
   float* buf[2] = {ar.take<float>(act), ar.take<float>(act)};
   float* pooled[4];
   for (int s = 0; s < 4; s++) pooled[s] = ar.take<float>((size_t)n_img * kSkipC[s]);
+  float* kseg_scratch = ar.take<float>((size_t)(n_img + 16) * H * W * 16);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
 
   // Tensor-core trunk: activations live as FP16 hi/lo NHWC planes between layers; the epilogue of one conv
@@ -263,7 +265,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
         const bool timed = mm_timing_on();   // roofline hook: the tcgen05 conv launches
         if (timed) mm_timing_begin(st, 2.0 * cout * 9.0 * cin * (double)n_img * h * w);
         MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
-                                    cur_plane, n_img, h, w, cin, hb[which], plane_out, st));
+                                    cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch));
         if (timed) mm_timing_end(st);
       }
       cur = hb[which]; cur_plane = plane_out; which ^= 1;

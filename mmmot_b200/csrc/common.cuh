@@ -27,6 +27,7 @@
 
 void mm_count_launch();
 int mm_debug_flags();
+int mm_kseg_chunks();  // K-segment length (in 32-wide chunks) of the tcgen05 conv engine, 0 = off (mmmot_set_kseg)
 int mm_engine();  // 0 auto, 1 FP32 FFMA engine, 2 tcgen05 engine (mmmot_set_engine)
 bool mm_timing_on();
 void mm_timing_begin(cudaStream_t st, double flop);

@@ -35,6 +35,8 @@ struct TmaP {
   int tiles_x, tiles_y;     // conv tile grid per image group
   int n_img, H, W, C;       // conv geometry (C = input channels)
   long plane_elems;         // output: distance (in fp16 elements) between the hi and lo planes
+  int ksegs, kc_per_seg;    // conv: K is accumulated in `ksegs` TMEM passes of kc_per_seg chunks whose fp32
+  float* acc_scratch;       // partial sums are combined in fp32 RN through acc_scratch[pixel][M] (see launcher)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
@@ -127,14 +129,67 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
     const int q = warp & 3, half = warp >> 2;
     uint32_t tphase = 0;
     __half* yh = reinterpret_cast<__half*>(p.Y);
+    const int lbx = 31 - __clz(max(P.bx, 1)), lby = 31 - __clz(max(P.by, 1));
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mg = (int)(t % mgroups);
       const int nt = (int)(t / mgroups);
       int g = 0, c0 = 0, len = BN, i0 = 0, y0 = 0, x0 = 0;
       if (P.conv) conv_origin(nt, i0, y0, x0); else tile_cols(nt, g, c0, len);
+      for (int seg = 0; seg < P.ksegs; seg++) {
       mbar_wait(tfull_bar, tphase);
       tphase ^= 1;
       tc_fence_after();
+      if (P.ksegs > 1) {
+        // K-segmented convolution: the tensor core's fp32 accumulator rounds toward zero at every K=16 step,
+        // so long K chains are cut into segments whose partial sums are combined here in fp32 round-to-nearest.
+        for (int mt = 0; mt < MT; mt++) {
+          const int co = (mg * MT + mt) * 128 + q * 32 + lane;
+          const bool rowok = co < p.M;
+          const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; cc++) {
+            const int col0 = half * 128 + cc * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
+            if (!rowok) continue;
+            // partial sums live in TILE order, scratch[(tile*256 + column)][M]: no pixel arithmetic, and a
+            // warp's 32 channels of one column are one 128-byte access
+            float* sp = P.acc_scratch + ((long)nt * BN + col0) * p.M + co;
+            if (seg < P.ksegs - 1) {
+              if (seg == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) __stcg(sp + (long)j * p.M, __uint_as_float(v[j]) * P.t.out_scale);
+              } else {
+                float sv[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) sv[j] = __ldcg(sp + (long)j * p.M);
+#pragma unroll
+                for (int j = 0; j < 32; j++) __stcg(sp + (long)j * p.M, fmaf(__uint_as_float(v[j]), P.t.out_scale, sv[j]));
+              }
+            } else {
+              float sv[32];
+#pragma unroll
+              for (int j = 0; j < 32; j++) sv[j] = __ldcg(sp + (long)j * p.M);
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const int col = col0 + j;
+                const int xx = col & (P.bx - 1), r = col >> lbx;
+                const int yy = r & (P.by - 1), ii = r >> lby;
+                const int img = i0 + ii, y = y0 + yy, x = x0 + xx;
+                if (img < P.n_img && y < P.H && x < P.W) {
+                  float a = fmaf(__uint_as_float(v[j]), P.t.out_scale, sv[j]) + bv;
+                  if (p.relu) a = fmaxf(a, 0.f);
+                  __half h, l;
+                  split_f16(a, h, l);
+                  const long o = (((long)img * P.H + y) * P.W + x) * p.y_ms + co;
+                  yh[o] = h;
+                  yh[o + P.plane_elems] = l;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int mt = 0; mt < MT; mt++) {
         const int co = (mg * MT + mt) * 128 + q * 32 + lane;
         const bool rowok = co < p.M;
@@ -214,15 +269,18 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
+      }
     }
   } else if (warp == T_MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
-      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, tcount++) {
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+       for (int seg = 0; seg < P.ksegs; seg++, tcount++) {
         mbar_wait(tempty_bar, (tcount & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < KC; kc++, it++) {
+        const int kc_lo = seg * P.kc_per_seg, kc_hi = min(KC, kc_lo + P.kc_per_seg);
+        for (int kc = kc_lo; kc < kc_hi; kc++, it++) {
           const int s = it % STAGES;
           mbar_wait(full_bar(s), (it / STAGES) & 1);
           tc_fence_after();
@@ -237,15 +295,16 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
                 const uint64_t b_hi = smem_desc_sw64(sb + ks * 32);
                 const uint64_t b_lo = smem_desc_sw64(sb + B_HALF + ks * 32);
                 const uint32_t d = tmem_base + (uint32_t)(mt * 256);
-                umma_f16(d, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
+                umma_f16(d, a_hi, b_hi, IDESC, ((kc - kc_lo) | ks) ? 1u : 0u);
                 umma_f16(d, a_hi, b_lo, IDESC, 1u);
                 umma_f16(d, a_lo, b_hi, IDESC, 1u);
               }
             }
           }
           umma_commit(empty_bar(s));
-          if (kc == KC - 1) umma_commit(tfull_bar);
+          if (kc == kc_hi - 1) umma_commit(tfull_bar);
         }
+       }
       }
     }
     __syncwarp();
@@ -358,6 +417,7 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.t.out_mode = out_mode;
   P.t.dbg = mm_debug_flags();
   P.plane_elems = y_plane;
+  P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));
@@ -370,8 +430,12 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
 }
 
 // 3x3 / pad 1 convolution on planar FP16 NHWC activations; output planar FP16 NHWC (ReLU via g.relu).
+// acc_scratch (fp32 [tiles*256][M], tiles = ceil(W/bx)*ceil(H/by)*ceil(n/bi) <= padded pixel count) enables K-segmentation: chains longer than mmmot_set_kseg() chunks of 32 are
+// accumulated in several TMEM passes and summed in fp32 RN, which bounds the tensor core's round-toward-zero
+// accumulation error.  nullptr = single pass.
 static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
-                                int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st) {
+                                int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st,
+                                float* acc_scratch = nullptr) {
   if (!Wp || C % tc::BK) return MMMOT_E_ARG;
   static int sms = 0;
   if (!sms) {
@@ -405,6 +469,13 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
   P.t.out_mode = tma::OUT_PLANAR;
   P.t.dbg = mm_debug_flags();
   P.plane_elems = y_plane;
+  P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
+  const int seg_chunks = mm_kseg_chunks();   // 0 = single pass
+  if (acc_scratch && seg_chunks > 0 && P.t.k_chunks > seg_chunks) {
+    P.ksegs = (P.t.k_chunks + seg_chunks - 1) / seg_chunks;
+    P.kc_per_seg = (P.t.k_chunks + P.ksegs - 1) / P.ksegs;
+    P.acc_scratch = acc_scratch;
+  }
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_4d(&mh, Xhi, n_img, H, W, C, bx, by, bi));
   MM_TRY(tma::make_map_4d(&ml, Xhi + x_plane, n_img, H, W, C, bx, by, bi));

@@ -54,6 +54,9 @@ try:
     ENG = os.environ.get("MMMOT_DIAG_ENGINE", "auto")
     mmmot_b200.set_engine(ENG)
     P("engine:", ENG)
+    if os.environ.get("MMMOT_KSEG"):
+        mmmot_b200._lib.load().mmmot_set_kseg(int(os.environ["MMMOT_KSEG"]))
+        P("kseg:", os.environ["MMMOT_KSEG"])
     for cfg in (("A", "multiply", "none", 8, 8, 32, 32, False, 1), ("C", "minus_abs", "dual_add", 6, 9, 24, 64, True, 2),
                 ("B", "multiply", "single", 16, 16, 64, 64, True, 3), ("C", "minus_abs", "dual_add", 32, 32, 128, 64, True, 4)):
         try:
