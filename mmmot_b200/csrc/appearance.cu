@@ -95,31 +95,30 @@ __global__ void plane_mean_planar_kernel(const __half* __restrict__ in, float* _
   out[idx] = s / (float)hw;
 }
 
-// First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound:
-// 1 MB of output per crop), so a direct FP32 FFMA kernel writes the FP16 hi/lo NHWC planes the next layer's
-// TMA loads read.  Each thread: 4 consecutive pixels x 16 channels (weights read from smem
-// once per 4 pixels as 128-bit loads); CTA = 64 pixel quads x 4 channel groups.  wt: [(ky*3+kx)*3 + ci][64]
-// (BN folded), ReLU fused.  W % 4 == 0.
-__global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
-                                                           const float* __restrict__ bias, long n_quads, int H, int W,
-                                                           __half* __restrict__ out, long plane) {
+// First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound: 1 MB of
+// output per crop), so a direct FP32 FFMA kernel writes the FP16 hi/lo NHWC planes the next layer's TMA loads
+// read.  Each thread: 2 horizontally adjacent pixels x 16 channels (weights from smem as 128-bit loads);
+// CTA = 64 pixel pairs x 4 channel groups.  wt: [(ky*3+kx)*3 + ci][64] (BN folded), ReLU fused.  W % 2 == 0.
+__global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
+                                                              const float* __restrict__ bias, long n_pairs, int H, int W,
+                                                              __half* __restrict__ out, long plane) {
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long quad = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const long pr = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
   const int cg = (threadIdx.x & 3) * 16;
-  if (quad >= n_quads) return;
-  const int wq = W >> 2, hw = H * W;
-  const long row = quad / wq;                // (img, y)
-  const int x0 = (int)(quad - row * wq) * 4;
+  if (pr >= n_pairs) return;
+  const int wp = W >> 1, hw = H * W;
+  const long row = pr / wp;                // (img, y)
+  const int x0 = (int)(pr - row * wp) * 2;
   const long img = row / H;
   const int y = (int)(row - img * H);
   const float* src = in + img * 3 * hw;
-  float acc[4][16];
+  float acc[2][16];
 #pragma unroll
-  for (int p = 0; p < 4; p++)
+  for (int p = 0; p < 2; p++)
 #pragma unroll
     for (int c = 0; c < 16; c++) acc[p][c] = bs[cg + c];
 #pragma unroll
@@ -129,28 +128,32 @@ __global__ void __launch_bounds__(256) conv0_packed_kernel(const float* __restri
       const int yy = y + ky - 1;
       const bool oky = yy >= 0 && yy < H;
       const float* rowp = src + (long)ci * hw + (long)yy * W + x0;
-      float v[6];
+      float v[4];
 #pragma unroll
-      for (int t = 0; t < 6; t++) {
+      for (int t = 0; t < 4; t++) {
         const int xx = x0 + t - 1;
         v[t] = (oky && xx >= 0 && xx < W) ? __ldg(rowp + t - 1) : 0.f;
       }
 #pragma unroll
       for (int kx = 0; kx < 3; kx++) {
         const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + ci) * 64 + cg);
-        float w[16];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const float4 t4 = wr[q]; w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w; }
+        for (int q = 0; q < 4; q++) {
+          const float4 t4 = wr[q];
 #pragma unroll
-        for (int p = 0; p < 4; p++)
-#pragma unroll
-          for (int c = 0; c < 16; c++) acc[p][c] = fmaf(v[p + kx], w[c], acc[p][c]);
+          for (int p = 0; p < 2; p++) {
+            acc[p][4 * q] = fmaf(v[p + kx], t4.x, acc[p][4 * q]);
+            acc[p][4 * q + 1] = fmaf(v[p + kx], t4.y, acc[p][4 * q + 1]);
+            acc[p][4 * q + 2] = fmaf(v[p + kx], t4.z, acc[p][4 * q + 2]);
+            acc[p][4 * q + 3] = fmaf(v[p + kx], t4.w, acc[p][4 * q + 3]);
+          }
+        }
       }
     }
   }
   const long pix0 = row * W + x0;
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
+  for (int p = 0; p < 2; p++) {
     __half h[16], l[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) tma::split_f16(fmaxf(acc[p][c], 0.f), h[c], l[c]);
@@ -253,7 +256,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       const int cout = kVggCout[i], cin = kVggCin[i];
       const long plane_out = (long)n_img * h * w * cout;
       if (i == 0) {
-        const long quads = (long)n_img * h * w / 4;
+        const long quads = (long)n_img * h * w / 2;   // pixel pairs
         conv0_packed_kernel<<<mm_cdiv(quads, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0], quads,
                                                                h, w, hb[which], plane_out);
         MM_LAUNCH_CHECK();

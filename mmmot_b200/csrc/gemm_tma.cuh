@@ -11,6 +11,9 @@
 //     no boundary code, no index arithmetic on the SMs.
 // CTA (320 threads, persistent, one per SM): warps 0-7 epilogue (two per TMEM lane quadrant, one per
 // column half), warp 8 MMA issuer, warp 9 loader (weights by cp.async.bulk, operand boxes by TMA).
+// When the tile has one 128-row subtile (Cout <= 128) the 512 TMEM columns hold TWO accumulator buffers, so
+// the epilogue of tile i overlaps the MMAs of tile i+1.  Conv outputs are transposed through a per-warp smem
+// scratch so each lane stores 64 contiguous bytes (32 channels of one pixel) per plane.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -24,7 +27,8 @@ using namespace tc;
 constexpr int T_THREADS = 320;
 constexpr int T_EPI_WARPS = 8, T_MMA_WARP = 8, T_LOAD_WARP = 9;
 constexpr int T_SCRATCH = 0;
-constexpr size_t T_SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int T_EPI_SCRATCH = 32 * 80;   // per epilogue warp: 32 pixels x (64 B of channels + 16 B pad)
+constexpr size_t T_SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + T_EPI_WARPS * T_EPI_SCRATCH;
 
 enum { OUT_PLANAR = 3 };   // two FP16 planes Y_hi[row][y_ms], Y_lo = Y_hi + plane_elems (channels-last)
 
@@ -81,8 +85,10 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
   const uint32_t bar0 = base + STAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES), tempty_bar = bar0 + 8u * (2 * STAGES + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2));
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  uint8_t* epi_scratch = sm + STAGES * STAGE_BYTES + 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = P.t.mt_per_cta;
@@ -91,14 +97,17 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
   // K chunks: conv = 9 taps x (C / 32) channel chunks, K order k = tap*C + ci ; matrix = K / 32
   const int KC = P.t.k_chunks;
   const int cchunks = P.conv ? P.C / BK : KC;
+  const int nbuf = (MT == 1) ? 2 : 1;   // accumulator buffers in TMEM (256 columns each when MT == 1)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(full_bar(s), 1);   // the loader's single expect_tx arrive (weights + 2 operand boxes)
       mbar_init(empty_bar(s), 1);  // tcgen05.commit
     }
-    mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, T_EPI_WARPS);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), T_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == T_MMA_WARP) {
@@ -127,17 +136,46 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
   if (warp < T_EPI_WARPS) {
     // =============================== EPILOGUE ===============================
     const int q = warp & 3, half = warp >> 2;
-    uint32_t tphase = 0;
-    __half* yh = reinterpret_cast<__half*>(p.Y);
     const int lbx = 31 - __clz(max(P.bx, 1)), lby = 31 - __clz(max(P.by, 1));
+    uint32_t wcount = 0;   // (tile, segment) work items processed by this CTA
+    __half* yh = reinterpret_cast<__half*>(p.Y);
+    __half* scr = reinterpret_cast<__half*>(epi_scratch + warp * T_EPI_SCRATCH);
+    // final conv values x[j] (pixel column col0+j, channel cb+lane) -> FP16 hi/lo NHWC planes.  The 32x32 block is
+    // transposed through smem so that lane p stores the 32 channels (64 contiguous bytes) of pixel col0+p.
+    auto store_planar_block = [&](const float (&x)[32], int col0, int cb, int i0, int y0, int x0) {
+      __half h[32], l[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) split_f16(x[j], h[j], l[j]);
+      const int col = col0 + lane;
+      const int xx = col & (P.bx - 1), r = col >> lbx;
+      const int yy = r & (P.by - 1), ii = r >> lby;
+      const int img = i0 + ii, y = y0 + yy, xg = x0 + xx;
+      const bool ok = img < P.n_img && y < P.H && xg < P.W;
+      const long o = (((long)img * P.H + y) * P.W + xg) * p.y_ms + cb;
+#pragma unroll
+      for (int pl = 0; pl < 2; pl++) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) scr[j * 40 + lane] = pl ? l[j] : h[j];
+        __syncwarp();
+        if (ok) {
+          const uint4* src = reinterpret_cast<const uint4*>(scr + lane * 40);
+          uint4* dst = reinterpret_cast<uint4*>(yh + o + (pl ? P.plane_elems : 0));
+          dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        }
+        __syncwarp();
+      }
+    };
+
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mg = (int)(t % mgroups);
       const int nt = (int)(t / mgroups);
       int g = 0, c0 = 0, len = BN, i0 = 0, y0 = 0, x0 = 0;
       if (P.conv) conv_origin(nt, i0, y0, x0); else tile_cols(nt, g, c0, len);
-      for (int seg = 0; seg < P.ksegs; seg++) {
-      mbar_wait(tfull_bar, tphase);
-      tphase ^= 1;
+      for (int seg = 0; seg < P.ksegs; seg++, wcount++) {
+      const int abuf = nbuf == 2 ? (int)(wcount & 1) : 0;
+      const uint32_t ause = nbuf == 2 ? (wcount >> 1) : wcount;
+      const uint32_t acc_col = (uint32_t)(abuf * 256);
+      mbar_wait(tfull_bar(abuf), ause & 1);
       tc_fence_after();
       if (P.ksegs > 1) {
         // K-segmented convolution: the tensor core's fp32 accumulator rounds toward zero at every K=16 step,
@@ -150,7 +188,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           for (int cc = 0; cc < 4; cc++) {
             const int col0 = half * 128 + cc * 32;
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * 256 + col0), v);
             if (!rowok) continue;
             // partial sums live in TILE order, scratch[(tile*256 + column)][M]: no pixel arithmetic, and a
             // warp's 32 channels of one column are one 128-byte access
@@ -172,20 +210,10 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
               for (int j = 0; j < 32; j++) sv[j] = __ldcg(sp + (long)j * p.M);
 #pragma unroll
               for (int j = 0; j < 32; j++) {
-                const int col = col0 + j;
-                const int xx = col & (P.bx - 1), r = col >> lbx;
-                const int yy = r & (P.by - 1), ii = r >> lby;
-                const int img = i0 + ii, y = y0 + yy, x = x0 + xx;
-                if (img < P.n_img && y < P.H && x < P.W) {
-                  float a = fmaf(__uint_as_float(v[j]), P.t.out_scale, sv[j]) + bv;
-                  if (p.relu) a = fmaxf(a, 0.f);
-                  __half h, l;
-                  split_f16(a, h, l);
-                  const long o = (((long)img * P.H + y) * P.W + x) * p.y_ms + co;
-                  yh[o] = h;
-                  yh[o + P.plane_elems] = l;
-                }
+                float a = fmaf(__uint_as_float(v[j]), P.t.out_scale, sv[j]) + bv;
+                sv[j] = p.relu ? fmaxf(a, 0.f) : a;
               }
+              store_planar_block(sv, col0, co - lane, i0, y0, x0);
             }
           }
         }
@@ -200,7 +228,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           const int col0 = half * 128 + cc * 32;
           if (col0 >= len) break;   // warp-uniform
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 256 + col0), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * 256 + col0), v);
           if (P.t.dbg & 1) continue;
           float s1 = 0.f, s2 = 0.f;
           bool fast = col0 + 32 <= len;
@@ -228,21 +256,10 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           d1 += (double)s1; d2 += (double)s2;
           if (!p.Y || !rowok) continue;
           if (P.conv) {
-            // column -> pixel of the box; planar FP16 (hi, lo) NHWC output
+            float xv[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int col = col0 + j;
-              const int xx = col % P.bx, r = col / P.bx;
-              const int yy = r % P.by, ii = r / P.by;
-              const int img = i0 + ii, y = y0 + yy, x = x0 + xx;
-              if (img < P.n_img && y < P.H && x < P.W) {
-                const long o = (((long)img * P.H + y) * P.W + x) * p.y_ms + co;
-                __half h, l;
-                split_f16(__uint_as_float(v[j]), h, l);
-                yh[o] = h;
-                yh[o + P.plane_elems] = l;
-              }
-            }
+            for (int j = 0; j < 32; j++) xv[j] = __uint_as_float(v[j]);
+            store_planar_block(xv, col0, co - lane, i0, y0, x0);
           } else {
             const int nvalid = min(32, len - col0);
             const long row0 = (long)g * p.y_gs + c0 + col0;
@@ -268,7 +285,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive(tempty_bar(abuf));
       }
     }
   } else if (warp == T_MMA_WARP) {
@@ -277,7 +294,9 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
       uint32_t it = 0, tcount = 0;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
        for (int seg = 0; seg < P.ksegs; seg++, tcount++) {
-        mbar_wait(tempty_bar, (tcount & 1) ^ 1);
+        const int abuf = nbuf == 2 ? (int)(tcount & 1) : 0;
+        const uint32_t ause = nbuf == 2 ? (tcount >> 1) : tcount;
+        mbar_wait(tempty_bar(abuf), (ause & 1) ^ 1);
         tc_fence_after();
         const int kc_lo = seg * P.kc_per_seg, kc_hi = min(KC, kc_lo + P.kc_per_seg);
         for (int kc = kc_lo; kc < kc_hi; kc++, it++) {
@@ -294,7 +313,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
                 const uint64_t a_lo = smem_desc(sa + mt * A_SUB + A_HALF + ks * 2 * A_LBO, A_LBO, SBO);
                 const uint64_t b_hi = smem_desc_sw64(sb + ks * 32);
                 const uint64_t b_lo = smem_desc_sw64(sb + B_HALF + ks * 32);
-                const uint32_t d = tmem_base + (uint32_t)(mt * 256);
+                const uint32_t d = tmem_base + (uint32_t)(abuf * 256 + mt * 256);
                 umma_f16(d, a_hi, b_hi, IDESC, ((kc - kc_lo) | ks) ? 1u : 0u);
                 umma_f16(d, a_hi, b_lo, IDESC, 1u);
                 umma_f16(d, a_lo, b_hi, IDESC, 1u);
@@ -302,7 +321,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
             }
           }
           umma_commit(empty_bar(s));
-          if (kc == kc_hi - 1) umma_commit(tfull_bar);
+          if (kc == kc_hi - 1) umma_commit(tfull_bar(abuf));
         }
        }
       }
@@ -324,10 +343,12 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           const int s = it % STAGES;
           mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
           const uint32_t abytes = (uint32_t)nmt * A_SUB;
-          mbar_expect_tx(full_bar(s), abytes + 2 * B_HALF);
+          const bool skipA = P.t.dbg & 2, skipB = P.t.dbg & 4;     // profiling experiments only
+          mbar_expect_tx(full_bar(s), (skipA ? 0u : abytes) + (skipB ? 0u : 2u * B_HALF));
           const uint32_t sa = base + s * STAGE_BYTES, sb = sa + 2 * A_SUB;
           const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t.Wp) + ((size_t)kc * P.t.m_tiles + mt0) * A_SUB;
-          bulk_g2s(sa, src, abytes, full_bar(s));
+          if (!skipA) bulk_g2s(sa, src, abytes, full_bar(s));
+          if (skipB) continue;
           if (P.conv) {
             const int tap = kc / cchunks, cc = kc - tap * cchunks;
             const int dx = tap % 3 - 1, dy = tap / 3 - 1;

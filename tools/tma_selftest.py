@@ -19,7 +19,10 @@ def planes(x):
     return torch.stack([hi, lo]).contiguous()
 
 
-for (M, K, rows) in ((128, 32, 256), (256, 64, 512), (512, 512, 4099), (64, 64, 300), (1024, 128, 1000), (512, 512, 148 * 256 * 4)):
+LIN = ((128, 32, 256), (256, 64, 512), (512, 512, 4099), (64, 64, 300), (1024, 128, 1000), (512, 512, 148 * 256 * 4))
+if os.environ.get('TMA_ONLY'):
+    LIN = ()
+for (M, K, rows) in LIN:
     Wt = torch.randn(K, M, generator=g); X = torch.randn(rows, K, generator=g); b = torch.randn(M, generator=g)
     ref = X.double() @ Wt.double() + b.double()
     Wp, wps = pack_tc(Wt)
@@ -35,8 +38,11 @@ for (M, K, rows) in ((128, 32, 256), (256, 64, 512), (512, 512, 4099), (64, 64, 
     err = float((Y.double().cpu() - ref).abs().max() / ref.abs().max())
     print(f"linear M={M} K={K} rows={rows}: rc={rc} err={err:.2e} {2.0*M*K*rows/dt/1e12:.1f} TF/s", flush=True)
 
-for (n, H, W, C, M) in ((4, 8, 8, 32, 64), (2, 64, 64, 64, 64), (3, 32, 32, 64, 128), (5, 16, 16, 128, 256), (9, 8, 8, 256, 512), (33, 4, 4, 512, 512),
-                        (2, 24, 40, 32, 64), (1024, 16, 16, 256, 256), (4096, 8, 8, 512, 512)):
+CONVS = ((4, 8, 8, 32, 64), (2, 64, 64, 64, 64), (3, 32, 32, 64, 128), (5, 16, 16, 128, 256), (9, 8, 8, 256, 512), (33, 4, 4, 512, 512),
+                        (2, 24, 40, 32, 64), (1024, 16, 16, 256, 256), (4096, 8, 8, 512, 512))
+if os.environ.get('TMA_ONLY'):
+    CONVS = ((1024, 64, 64, 64, 64), (1024, 32, 32, 128, 128), (1024, 16, 16, 256, 256))
+for (n, H, W, C, M) in CONVS:
     w = torch.randn(M, C, 3, 3, generator=g) * (2.0 / (9 * C)) ** 0.5
     b = torch.randn(M, generator=g) * 0.1
     x = torch.randn(n, C, H, W, generator=g)
