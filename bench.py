@@ -14,8 +14,8 @@ the assignment indices, inside the timed region.
 value : frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks).
 e2e   : same metric through the public API with HOST (pinned) inputs: H2D of crops/points and D2H
         of the assignment results inside the timed region.
-roofline: dominant kernel = tc::gemm_tc_kernel<XM_CONV3S>, the tcgen05 3x3-conv contraction of the VGG
-        trunk (12 launches per chunk, 83 % of the algorithmic FLOPs, ~56 % of the step), timed per launch
+roofline: dominant kernel = tma::gemm_tma_kernel in conv mode, the TMA-fed tcgen05 3x3-conv contraction of the
+        VGG trunk (12 launches per chunk, 83 % of the algorithmic FLOPs, ~50 % of the step), timed per launch
         with CUDA events on the launching stream (library hook mmmot_timing_*).
 cpu_baseline / --impl reference: the oracle port of the reference's PyTorch-CPU path (the reference
         is pure Python and /root/reference does not exist on the GPU box) on all host cores.
@@ -209,18 +209,43 @@ def main():
             dist.all_gather(gathered, o["match"])
         return o
 
+    # e2e: pinned host -> device copies are pipelined against compute in sub-batches (copy stream + events);
+    # every byte of every step's inputs crosses PCIe inside the timed region, results come back D2H.
+    nsub = 4 if B % 4 == 0 and B >= 8 else 1
+    sb = B // nsub
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(nsub)]
+    ev_used = [torch.cuda.Event() for _ in range(nsub)]
+    sub_split = torch.arange(0, sb * L * pts + 1, pts, dtype=torch.int32)
+    for e in ev_used:
+        e.record()
+
     def step_e2e():
-        d_crops2.copy_(h_crops, non_blocking=True)
-        d_points2.copy_(h_points, non_blocking=True)
-        o = net.predict_batch(d_crops2, d_points2, split, n)
-        h_match.copy_(o["match"], non_blocking=True)
-        h_flags[0].copy_(o["assign_det"], non_blocking=True)
-        h_flags[1].copy_(o["assign_new"], non_blocking=True)
-        h_flags[2].copy_(o["assign_end"], non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        for i in range(nsub):
+            c0, c1 = i * sb * L, (i + 1) * sb * L
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_used[i])             # previous step finished reading this slice
+                d_crops2[c0:c1].copy_(h_crops[c0:c1], non_blocking=True)
+                d_points2[c0 * pts:c1 * pts].copy_(h_points[c0 * pts:c1 * pts], non_blocking=True)
+                ev_copied[i].record(copy_stream)
+        outs = []
+        for i in range(nsub):
+            c0, c1 = i * sb * L, (i + 1) * sb * L
+            cur.wait_event(ev_copied[i])
+            o = net.predict_batch(d_crops2[c0:c1], d_points2[c0 * pts:c1 * pts], sub_split, n)
+            ev_used[i].record(cur)
+            p0, p1 = i * sb, (i + 1) * sb
+            h_match[p0:p1].copy_(o["match"], non_blocking=True)
+            h_flags[0, p0:p1].copy_(o["assign_det"], non_blocking=True)
+            h_flags[1, p0:p1].copy_(o["assign_new"], non_blocking=True)
+            h_flags[2, p0:p1].copy_(o["assign_end"], non_blocking=True)
+            outs.append(o["match"])
         if world > 1:
-            gathered = [torch.empty_like(o["match"]) for _ in range(world)]
-            dist.all_gather(gathered, o["match"])
-        return o
+            allm = torch.cat(outs, 0)
+            gathered = [torch.empty_like(allm) for _ in range(world)]
+            dist.all_gather(gathered, allm)
+        return outs
 
     def timed(fn, steps, warmup, with_hooks=False):
         for _ in range(warmup):
@@ -279,11 +304,12 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "tensor",
-                    "kernel": ("tc::gemm_tc_kernel<XM_CONV3S> (tcgen05 3x3-conv contraction of the VGG trunk, FP16 hi/lo "
-                               "split: 3 MMAs per algorithmic MAC)") if tc_engine else
+                    "kernel": ("tma::gemm_tma_kernel, conv mode (TMA-fed tcgen05 3x3-conv contraction of the VGG trunk, FP16 "
+                               "hi/lo split: 3 MMAs per algorithmic MAC)") if tc_engine else
                               "gemm_simt_kernel<XM_CONV3> (VGG 3x3 conv contraction, FP32 FFMA engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "mma_issue_tflops": 3 * achieved if tc_engine else None,
+                    "mma_issue_frac": 3 * achieved / peak if tc_engine else None,
                     "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step); 'achieved' counts "
                                    "ALGORITHMIC FLOPs (2*Cout*9Cin*pixels per launch); the tensor pipe executes 3x that",
                     "launches_timed": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),

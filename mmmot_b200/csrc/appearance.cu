@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __res
   for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long pr = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
-  const int cg = (threadIdx.x & 3) * 16;
+  // warp-uniform channel group (weight reads are smem broadcasts); lanes = 32 consecutive pixel pairs
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long pr = (long)blockIdx.x * 64 + (warp >> 2) * 32 + lane;
+  const int cg = (warp & 3) * 16;
   if (pr >= n_pairs) return;
   const int wp = W >> 1, hw = H * W;
   const long row = pr / wp;                // (img, y)
