@@ -466,10 +466,17 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
     MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)tma::T_SMEM_BYTES));
   }
-  // box of 256 pixels: as wide as the image allows (power of two), then rows, then images
-  int bx = 1; while (bx * 2 <= W && bx * 2 <= 256) bx *= 2;
-  int by = 1; while (by * 2 <= H && bx * by * 2 <= 256) by *= 2;
-  const int bi = 256 / (bx * by);
+  // box of 256 pixels = bx * by * bi (powers of two): the shape with the least padding waste, widest first
+  int bx = 1, by = 1, bi = 256;
+  {
+    double best = 1e30;
+    for (int cx = 256; cx >= 1; cx >>= 1)
+      for (int cy = 256 / cx; cy >= 1; cy >>= 1) {
+        const int ci = 256 / (cx * cy);
+        const double waste = (double)mm_cdiv(W, cx) * cx / W * mm_cdiv(H, cy) * cy / H * mm_cdiv(n_img, ci) * ci / n_img;
+        if (waste < best - 1e-9) { best = waste; bx = cx; by = cy; bi = ci; }
+      }
+  }
   tma::TmaP P;
   memset(&P, 0, sizeof(P));
   GemmP g = g0;

@@ -91,6 +91,27 @@ def test_affinity_stage_matches_oracle(n, m, op, sm, engine):
         assert relerr(new[b], rn) < TOL and relerr(end[b], re) < TOL
 
 
+@pytest.mark.parametrize("hw,n", [(96, 3), (224, 1)])
+def test_non_power_of_two_crops(hw, n, engine):
+    """Crop sizes that are multiples of 32 but not powers of two (224 is the reference's real crop size,
+    dataset/test_seq_dataset.py:217-218): partial TMA boxes / tile tails."""
+    net, sd = make_net("A", "multiply", "none", 0.2, 12)
+    dets, info, split = synthetic_pair(n, n, 32, hw, seed=50 + hw)
+    o = net.forward_batch(dets.cuda(), info["points"][0].cuda(), info["points_split"][0], n, n, keep_feats=True)
+    _, st = torch_ref.forward(sd, dets, info, split, "A", "multiply", "none", 0.2, return_stages=True)
+    assert relerr(o["feats"][0, 0], st["feats"][0]) < TOL
+
+
+def test_affinity_n256_top_of_sweep():
+    """BASELINE config 5, N = 256 (top of the N sweep), one pair, tensor-core engine vs oracle."""
+    net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 7)
+    g = torch.Generator().manual_seed(256)
+    feats = torch.relu(torch.randn(1, 3, 512, 512, generator=g))
+    link, new, end = net.associate_batch(feats.cuda(), 256, 256)
+    rl, rn, re = torch_ref.associate(sd, feats[0, :, :, :256], feats[0, :, :, 256:], "minus_abs", "dual_add")
+    assert relerr(link[0], rl.squeeze(1)) < TOL and relerr(new[0], rn) < TOL and relerr(end[0], re) < TOL
+
+
 def test_batched_equals_looped():
     """forward_batch over B pairs == B single-pair forwards (pairs are independent GroupNorm domains)."""
     net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 5)
