@@ -255,7 +255,7 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   AfWs w = carve(ar, pairs, n, m);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
   const int G = pairs * 3, NM = n * m, L = n + m;
-  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && (long)G * NM >= 4096);
+  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && NM >= 256);   // per-pair shape only (see appearance.cu)
   const int tpg = mm_cdiv(NM, use_tc ? tc::BN : 128);
   const float* const* W = wts->w;
 

@@ -248,7 +248,9 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
 
   // Tensor-core trunk: activations live as FP16 hi/lo NHWC planes between layers; the epilogue of one conv
   // writes exactly what the next conv's TMA loads read (3x3 taps = shifted boxes, padding = TMA zero fill).
-  const bool tc_trunk = mm_engine() == 2 || (mm_engine() == 0 && (long)n_img * H * W >= 65536);
+  // engine choice depends on per-pair shapes only (never on the batch size), so batched, looped and sharded runs
+  // take the same path and stay bit-identical
+  const bool tc_trunk = mm_engine() == 2 || (mm_engine() == 0 && (long)L * H * W >= 32768);
   if (tc_trunk) {
     __half* hb[2] = {reinterpret_cast<__half*>(buf[0]), reinterpret_cast<__half*>(buf[1])};
     const __half* cur = nullptr;

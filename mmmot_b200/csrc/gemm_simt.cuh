@@ -16,9 +16,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { XM_DIRECT = 0, XM_NORM_RELU = 1, XM_PAIR_MUL = 2, XM_PAIR_ABS = 3, XM_PAIR_SUB = 4, XM_CONV3 = 5,
-       XM_CONV3S = 6, /* tcgen05 engine only: 3x3 conv on packed FP16 (hi|lo) NHWC activations */
-       XM_PACKED = 7  /* tcgen05 engine only: X[row][Cin] packed FP16 (hi|lo) channels-last words */ };
+enum { XM_DIRECT = 0, XM_NORM_RELU = 1, XM_PAIR_MUL = 2, XM_PAIR_ABS = 3, XM_PAIR_SUB = 4, XM_CONV3 = 5 };
 
 struct GemmP {
   // A operand: transposed weights Wt[K][ldw], output channels [m_base, m_base + M)

@@ -12,9 +12,8 @@
 // Persistent, warp-specialised CTA (one per SM), tile 256 (M) x 256 (N), K chunks of 32:
 //   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = output channel; warp w owns TMEM
 //               lanes 32*w..), bias / addend / ReLU, per-thread GroupNorm
-//               partial sums (no shuffles).  Outputs are channels-last ([column][channel]: fp32, or
-//               packed FP16 hi|lo words for the next tensor-core layer), so a warp's 32 channels
-//               make one 128-byte store; the legacy fp32 [C][S] layout is transposed through smem.
+//               partial sums (no shuffles).  Channels-last fp32 outputs ([column][channel]) make a
+//               warp's 32 channels one 128-byte store; the fp32 [C][S] layout is transposed through smem.
 //   warp  4     MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16), 12 per
 //               chunk; accumulators (2 x 256 fp32 columns) live in TMEM; owns TMEM alloc/dealloc
 //   warp  5     A loader: one thread, cp.async.bulk (TMA engine, no tensor map) of pre-packed
@@ -22,9 +21,7 @@
 //   warps 6-13  B producers: generate the operand tile (plain load / GroupNorm+ReLU of the
 //               producer layer / pairwise op / 3x3 im2col), split to FP16 hi/lo and write it to
 //               shared memory in the UMMA canonical K-major (no-swizzle) core-matrix layout.
-//               XM_CONV3S / XM_PACKED read activations already stored as packed FP16 (hi|lo)
-//               channels-last words (by the previous layer's epilogue or by the GroupNorm+ReLU
-//               split pass): 128-bit loads, byte-permute de-interleave, no conversion.
+//               (Operands that already exist as FP16 hi/lo planes are fed by TMA instead: gemm_tma.cuh.)
 // 3-stage smem ring (64 KB per stage), mbarrier full/empty pipeline, tcgen05.commit releases stages.
 #pragma once
 #include "gemm_simt.cuh"
@@ -125,8 +122,7 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
-enum { OUT_CS = 0,        // fp32 Y[g][co][s]   (legacy layout of the FP32 engine; transposed through smem)
-       OUT_PACKED = 1,    // uint32 Y[row][M] packed FP16 (hi | lo << 16), row = g*y_gs + column
+enum { OUT_CS = 0,        // fp32 Y[g][co][s]   (layout of the FP32 engine; transposed through smem)
        OUT_CL = 2 };      // fp32  Y[row][y_ms] channels-last, row = g*y_gs + column
 
 struct TcP {
@@ -140,20 +136,6 @@ struct TcP {
   int dbg;             // profiling experiments only (mmmot_set_debug): 1 skip epilogue work, 2 skip A loads,
                        // 4 skip B generation, 8 skip MMA issue
 };
-
-// fp32 -> packed (hi | lo << 16) FP16 pair with x ~= hi + lo
-__device__ __forceinline__ uint32_t pack_split_f16(float x) {
-  uint32_t r;
-  asm("{\n\t.reg .b16 a, b;\n\t.reg .f32 f;\n\t"
-      "cvt.rn.satfinite.f16.f32 a, %1;\n\t"
-      "cvt.f32.f16 f, a;\n\t"
-      "sub.f32 f, %1, f;\n\t"
-      "cvt.rn.satfinite.f16.f32 b, f;\n\t"
-      "mov.b32 %0, {a, b};\n\t}"
-      : "=r"(r)
-      : "f"(x));
-  return r;
-}
 
 template <bool RELU>
 __device__ __forceinline__ void epi_fast(uint32_t (&v)[32], float scale, float bv, float& s1, float& s2) {
@@ -213,7 +195,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
     const int q = warp & 3;   // TMEM lane quadrant owned by this warp
     uint32_t tphase = 0;
     float* sc = scratch + warp * (32 * 33);
-    uint32_t* ypk = reinterpret_cast<uint32_t*>(p.Y);
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mg = (int)(t % mgroups);
       const int nt = (int)(t / mgroups);
@@ -280,12 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
           } else if (rowok) {
             // channels-last: a warp's 32 consecutive channels of one column = one 128-byte store
             const int nvalid = min(32, len - col0);
-            if (P.out_mode == OUT_PACKED) {
-              uint32_t* dst = ypk + ((long)g * p.y_gs + c0 + col0) * p.y_ms + co;
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (j < nvalid) dst[(long)j * p.y_ms] = pack_split_f16(__uint_as_float(v[j]));
-            } else {
+            {
               float* dst = p.Y + ((long)g * p.y_gs + c0 + col0) * p.y_ms + co;
 #pragma unroll
               for (int j = 0; j < 32; j++)
@@ -376,95 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const TcP P) {
       if (lane == 0) mbar_arrive(full_bar(s));
     };
 
-    if (MODE == XM_CONV3S || MODE == XM_PACKED) {
-      // ---- packed-FP16 channels-last activations: item = (row, k-group of 8 channels) = 32 contiguous bytes.
-      //      XM_CONV3S: rows are NHWC pixels, 9 taps (K order k = tap*Cin + ci, Cin % 32 == 0)
-      //      XM_PACKED: rows are columns of X[row][Cin words], one tap (K <= Cin, K % 32 == 0)
-      const uint32_t* X = reinterpret_cast<const uint32_t*>(p.X);
-      const int kg = pt & 3;
-      long pbase[4];   // word offset of this thread's 4 rows
-      int pmask[4];    // tap validity bits
-      auto gather = [&](uint4 (&w)[8]) {
-        if (gi >= my_chunks) { gi++; return; }
-        const int kc = (int)(gi % KC);
-        if (kc == 0) {
-          int g, c0, len;
-          tile_cols(gi, g, c0, len);
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int pl = (pt >> 2) + 64 * i;
-            if (MODE == XM_CONV3S) {
-              const int hw = p.H * p.W;
-              const int s = c0 + pl;
-              const int img = s / hw, pix = s - img * hw;
-              const int y = pix / p.W, x = pix - y * p.W;
-              pbase[i] = (long)s * p.Cin;
-              int mk = 0;
-#pragma unroll
-              for (int tp = 0; tp < 9; tp++) {
-                const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-                if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) mk |= 1 << tp;
-              }
-              pmask[i] = pl < len ? mk : 0;
-            } else {
-              pbase[i] = ((long)g * p.x_gs + c0 + pl) * p.Cin;
-              pmask[i] = pl < len ? 1 : 0;
-            }
-          }
-        }
-        gi++;
-        if (P.dbg & 4) return;
-        const int k0 = kc * BK;
-        int tap = 0;
-        long d = k0 + kg * 8;
-        if (MODE == XM_CONV3S) {
-          tap = k0 / p.Cin;
-          d = (long)((tap / 3 - 1) * p.W + (tap % 3 - 1)) * p.Cin + (k0 - tap * p.Cin) + kg * 8;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if ((pmask[i] >> tap) & 1) {
-            const uint4* src = reinterpret_cast<const uint4*>(X + pbase[i] + d);
-            w[2 * i] = __ldg(src);
-            w[2 * i + 1] = __ldg(src + 1);
-          } else {
-            w[2 * i] = make_uint4(0, 0, 0, 0);
-            w[2 * i + 1] = make_uint4(0, 0, 0, 0);
-          }
-        }
-      };
-      auto publish = [&](long it, const uint4 (&w)[8]) {
-        const int s = (int)(it % STAGES);
-        mbar_wait(empty_bar(s), (uint32_t)((it / STAGES) & 1) ^ 1u);
-        uint8_t* bh = sm + s * STAGE_BYTES + 2 * A_SUB + kg * B_LBO;
-        if (!(P.dbg & 4)) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int pl = (pt >> 2) + 64 * i;
-            const uint32_t off = (uint32_t)(pl >> 3) * 128u + (uint32_t)(pl & 7) * 16u;
-            const uint4 a = w[2 * i], b = w[2 * i + 1];
-            // word = hi | lo << 16  ->  separate hi / lo streams
-            *reinterpret_cast<uint4*>(bh + off) =
-                make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410),
-                           __byte_perm(b.x, b.y, 0x5410), __byte_perm(b.z, b.w, 0x5410));
-            *reinterpret_cast<uint4*>(bh + B_HALF + off) =
-                make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632),
-                           __byte_perm(b.x, b.y, 0x7632), __byte_perm(b.z, b.w, 0x7632));
-          }
-        }
-        arrive_full(s);
-      };
-      uint4 wa[8], wb[8];
-      gather(wa);
-      for (long it = 0; it < my_chunks; it += 2) {
-        gather(wb);
-        publish(it, wa);
-        if (it + 1 < my_chunks) {
-          gather(wa);
-          publish(it + 1, wb);
-        }
-      }
-    } else {
+    {
       // ---- fp32 sources: one thread per tile column, 32 k per chunk ----
       const int col = pt;
       const uint32_t row_off = (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;

@@ -140,7 +140,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     if (h_det_split[d + 1] <= h_det_split[d]) return MMMOT_E_SHAPE;  // every detection owns >= 1 point
 
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
-  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && P >= 4096);
+  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && L >= 16);   // per-pair shape only (see appearance.cu)
   const int TNW = use_tc ? tc::BN : 128;
   std::vector<int4> tiles;
   std::vector<int> cnt(pairs), gstart(pairs + 1);
