@@ -3,6 +3,7 @@ forward behind the reference's own Python surface.  See DESIGN.md."""
 from .config import build_model, model_kwargs  # noqa: F401
 from .solvers import ortools_solve, solve_batch  # noqa: F401
 from .tracking_net import TrackingNet  # noqa: F401
+from .lidar_crop import box_camera_to_lidar, box_planes, crop_points  # noqa: F401
 
 
 def set_engine(engine):

@@ -63,6 +63,9 @@ SIGNATURES = {
     "mmmot_fusion_det_fwd": (_i, [_wp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_affinity_workspace": (_sz, [_i, _i, _i]),
     "mmmot_affinity_fwd": (_i, [_wp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_crop_workspace": (_sz, [_i, _i]),
+    "mmmot_crop_count": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "mmmot_crop_scatter": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "mmmot_lp_workspace": (_sz, [_i, _i, _i]),
     "mmmot_lp_assign": (_i, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

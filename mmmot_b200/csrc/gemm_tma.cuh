@@ -41,6 +41,8 @@ struct TmaP {
   long plane_elems;         // output: distance (in fp16 elements) between the hi and lo planes
   int ksegs, kc_per_seg;    // conv: K is accumulated in `ksegs` TMEM passes of kc_per_seg chunks whose fp32
   float* acc_scratch;       // partial sums are combined in fp32 RN through acc_scratch[pixel][M] (see launcher)
+  unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
+                            // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
@@ -254,6 +256,33 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
             }
           }
           d1 += (double)s1; d2 += (double)s2;
+          if (P.segsum && rowok) {
+            // GroupNorm + ReLU + per-detection sum fused into the (recomputing) second pass: the activation never
+            // reaches HBM.  Run sums are fp32 in column order; runs are merged with integer atomics, so the result
+            // does not depend on the order in which tiles finish.
+            const float na = __ldg(p.sc + (long)g * p.M + co), nb = __ldg(p.sh + (long)g * p.M + co);
+            const int nvalid = min(32, len - col0);
+            int dcur = __ldg(p.seg + c0 + col0);
+            float run = 0.f;
+            if (nvalid == 32 && __ldg(p.seg + c0 + col0 + 31) == dcur) {
+              // common case: the whole 32-column chunk belongs to one detection
+#pragma unroll
+              for (int j = 0; j < 32; j++) run += fmaxf(fmaf(__uint_as_float(v[j]), na, nb), 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                if (j < nvalid) {
+                  const int d = __ldg(p.seg + c0 + col0 + j);
+                  if (d != dcur) {
+                    atomicAdd(P.segsum + (long)dcur * p.M + co, __float2ull_rn(run * 4294967296.f));
+                    run = 0.f; dcur = d;
+                  }
+                  run += fmaxf(fmaf(__uint_as_float(v[j]), na, nb), 0.f);
+                }
+              }
+            }
+            atomicAdd(P.segsum + (long)dcur * p.M + co, __float2ull_rn(run * 4294967296.f));
+          }
           if (!p.Y || !rowok) continue;
           if (P.conv) {
             float xv[32];
@@ -417,7 +446,8 @@ static inline int make_map_4d(CUtensorMap* m, const void* basep, int n_img, int 
 // 1x1 contraction on planar FP16 (hi, lo) channels-last activations X_hi[rows][ldx], X_lo = X_hi + x_plane.
 // g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
 static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
-                               long rows, int ldx, int out_mode, long y_plane, cudaStream_t st) {
+                               long rows, int ldx, int out_mode, long y_plane, cudaStream_t st,
+                               unsigned long long* segsum = nullptr) {
   if (!Wp || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
   static int sms = 0;
   if (!sms) {
@@ -439,6 +469,7 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.t.dbg = mm_debug_flags();
   P.plane_elems = y_plane;
   P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
+  P.segsum = segsum;
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));

@@ -12,27 +12,39 @@
 // Fixed-order reduction of the contraction engine's per-tile partials: stats[g][c] = sum over the
 // group's tiles (ascending) of part[tile][c].  Group g owns tiles [g*tpg, (g+1)*tpg) (uniform) or
 // [gstart[g], gstart[g+1]) (table tiling).
-// `mult` = partials per tile (1 for the FP32 engine, 2 for the tcgen05 engine).
-static __global__ void stats_reduce_kernel(const double2* __restrict__ part, int M, int G, int tpg,
-                                           const int* __restrict__ gstart, int mult,
-                                           double* __restrict__ stats) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= G * M) return;
-  int g = idx / M, c = idx - g * M;
-  int t0 = (gstart ? gstart[g] : g * tpg) * mult, t1 = (gstart ? gstart[g + 1] : (g + 1) * tpg) * mult;
+// `mult` = partials per tile (1 for the FP32 engine, 2 for the tcgen05 engines).
+// CTA = 32 channels x 8 tile stripes: stripe y sums tiles t0+y, t0+y+8, ... in order, then the 8 stripe sums are
+// added in stripe order -> a fixed summation tree, independent of scheduling.
+static __global__ void __launch_bounds__(256) stats_reduce_kernel(const double2* __restrict__ part, int M, int G,
+                                                                  int tpg, const int* __restrict__ gstart, int mult,
+                                                                  double* __restrict__ stats) {
+  __shared__ double2 red[8][32];
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = (gstart ? gstart[g] : g * tpg) * mult, t1 = (gstart ? gstart[g + 1] : (g + 1) * tpg) * mult;
   double s1 = 0.0, s2 = 0.0;
-  for (int t = t0; t < t1; t++) {
-    double2 v = part[(long)t * M + c];
-    s1 += v.x;
-    s2 += v.y;
+  if (c < M) {
+    for (int t = t0 + threadIdx.y; t < t1; t += 8) {
+      const double2 v = part[(long)t * M + c];
+      s1 += v.x;
+      s2 += v.y;
+    }
   }
-  stats[(long)idx * 2] = s1;
-  stats[(long)idx * 2 + 1] = s2;
+  red[threadIdx.y][threadIdx.x] = make_double2(s1, s2);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < M) {
+    double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) { a1 += red[y][threadIdx.x].x; a2 += red[y][threadIdx.x].y; }
+    stats[((long)g * M + c) * 2] = a1;
+    stats[((long)g * M + c) * 2 + 1] = a2;
+  }
 }
 
 static inline int stats_reduce(const double2* part, int M, int G, int tpg, const int* gstart, double* stats,
                                cudaStream_t st, int mult = 1) {
-  stats_reduce_kernel<<<mm_cdiv((long)G * M, 128), 128, 0, st>>>(part, M, G, tpg, gstart, mult, stats);
+  dim3 grid(mm_cdiv(M, 32), G), block(32, 8);
+  stats_reduce_kernel<<<grid, block, 0, st>>>(part, M, G, tpg, gstart, mult, stats);
   MM_LAUNCH_CHECK();
   return 0;
 }

@@ -81,8 +81,19 @@ __global__ void segment_mean_cl_kernel(const float* __restrict__ Y, int C, const
   }
 }
 
+// out[c][d] = segsum[d][c] * 2^-32 / (points of detection d)   (fixed-point sums of the fused segment-sum epilogue)
+__global__ void segsum_mean_kernel(const unsigned long long* __restrict__ segsum, const int* __restrict__ split,
+                                   int C, int ndet, float* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)C * ndet) return;
+  const int d = (int)(idx / C), c = (int)(idx - (long)d * C);
+  const int cnt = split[d + 1] - split[d];
+  out[(long)c * ndet + d] = cnt > 0 ? (float)((double)segsum[idx] * (1.0 / 4294967296.0) / (double)cnt) : 0.f;
+}
+
 struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *ut, *hmean, *o;
+  unsigned long long* segsum;   // tensor-core path: [ndet][1024] fixed-point per-detection sums
   __half *x1p, *xp;     // tensor-core path: FP16 hi/lo planes of normalised activations [2][P][64], [2][P][128]
   float *sc1, *sh1, *sc, *sh;
   double* stats;
@@ -99,6 +110,7 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
   w.t0 = a.take<float>(128 * P);
   w.t1 = a.take<float>(64 * P);
   w.big = a.take<float>(1024 * P);
+  w.segsum = a.take<unsigned long long>(1024 * nd);
   w.x1p = a.take<__half>(2 * 64 * P);
   w.xp = a.take<__half>(2 * 128 * P);
   w.gmean = a.take<float>(1024 * nd);
@@ -169,13 +181,13 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     // ---------------- tensor-core path: channels-last activations ----------------
     // layer i writes fp32 Y[p][cout] + GroupNorm partials; norm_split turns it into the packed FP16
     // operand of layer i+1.  y1's packed form (x1p) is kept for the head.
-    float* ybuf[5] = {w.y1, w.t0, w.t1, w.t0, w.big};
+    float* ybuf[5] = {w.y1, w.t0, w.t1, w.t0, nullptr};
     for (int i = 0; i < 5; i++) {
       const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
       GemmP p = gemm_defaults();
       p.bias = q[1]; p.M = cout[i]; p.K = cin[i];
       p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
-      p.Y = ybuf[i]; p.y_ms = cout[i];
+      p.Y = ybuf[i]; p.y_ms = cout[i];       // layer 5 (1024 wide): statistics only, nothing stored
       p.part = w.part;
       const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
       const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
@@ -187,11 +199,19 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       }
       MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
-      if (i < 4)
+      if (i < 4) {
         MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, st));
+      } else {
+        // second pass of the 1024-wide layer: recompute, GroupNorm + ReLU + per-detection mean in the epilogue
+        // (its 1024 x P activation, 537 MB per frame-pair at cfg4, is never written)
+        MM_CUDA(cudaMemsetAsync(w.segsum, 0, (size_t)ndet * 1024 * sizeof(unsigned long long), st));
+        p.Y = nullptr; p.part = nullptr;
+        p.sc = w.sc; p.sh = w.sh; p.seg = w.seg;
+        MM_TRY(gemm_tma_launch_mat(p, wp, wps, w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st, w.segsum));
+        segsum_mean_kernel<<<mm_cdiv(1024L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 1024, ndet, w.gmean);
+        MM_LAUNCH_CHECK();
+      }
     }
-    segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 1024, det_split, w.sc, w.sh, ndet, L, w.gmean);
-    MM_LAUNCH_CHECK();
     {
       GemmP p = gemm_defaults();
       p.Wt = wts->w[MMMOT_W_PN_WHGT]; p.ldw = 512; p.M = 512; p.K = 1024;
@@ -205,14 +225,19 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       GemmP p = gemm_defaults();
       p.bias = wts->w[MMMOT_W_PN_BH]; p.M = 512; p.K = 64;
       p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
-      p.Y = w.big; p.y_ms = 512;
+      p.Y = nullptr; p.y_ms = 512;           // pass 1: statistics only
       p.part = w.part;
       p.addend = w.ut; p.seg = w.seg; p.ld_add = 512;
-      MM_TRY(gemm_tma_launch_mat(p, (const uint4*)wts->w[MMMOT_W_PN_WHAP], wts->tc_scale[MMMOT_W_PN_WHAP], w.x1p, P * 64, P,
-                                 64, tc::OUT_CL, 0, st));
+      const uint4* whp = (const uint4*)wts->w[MMMOT_W_PN_WHAP];
+      const float whs = wts->tc_scale[MMMOT_W_PN_WHAP];
+      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st));
       MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1, w.sc, w.sh, st));
-      segment_mean_cl_kernel<<<ndet, 256, 0, st>>>(w.big, 512, det_split, w.sc, w.sh, ndet, L, w.hmean);
+      // pass 2: recompute + GroupNorm + ReLU + per-detection mean
+      MM_CUDA(cudaMemsetAsync(w.segsum, 0, (size_t)ndet * 512 * sizeof(unsigned long long), st));
+      p.part = nullptr; p.sc = w.sc; p.sh = w.sh;
+      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, w.segsum));
+      segsum_mean_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 512, ndet, w.hmean);
       MM_LAUNCH_CHECK();
     }
   } else {

@@ -48,8 +48,47 @@ def reference_forward(case, want_feats=False):
             "trans1": trans[0], "trans2": trans[1], "feats": feats}
 
 
+def crop_goldens():
+    """LiDAR cropping through the UNMODIFIED reference functions (numba):
+    box_np_ops.box_camera_to_lidar + preprocess.remove_points_outside_boxes, per box, empty box -> zero point."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, ref_loader.REF)
+    from point_cloud import box_np_ops
+    from point_cloud.preprocess import remove_points_outside_boxes
+    for name, P, n, seed in (("crop_small", 3000, 7, 1), ("crop_mid", 20000, 24, 7)):
+        rng = np.random.default_rng(seed)
+        centers = rng.uniform([0, -20, -2], [60, 20, 0], size=(n, 3)).astype(np.float32)
+        pts = np.concatenate([centers[rng.integers(0, n, P)] + rng.normal(size=(P, 3)) * [2.0, 1.2, 0.9],
+                              rng.uniform(size=(P, 1))], 1).astype(np.float32)
+        boxes = np.concatenate([centers, rng.uniform([1.2, 2.5, 1.2], [2.2, 5.0, 2.0], size=(n, 3)),
+                                rng.uniform(-3.14, 3.14, size=(n, 1))], 1).astype(np.float32)
+        boxes[n // 2, :3] += 1000.0                       # one empty box
+        out, split = [], [0]
+        for i in range(n):
+            bp = remove_points_outside_boxes(pts, boxes[i:i + 1])
+            if bp.shape[0] == 0:
+                bp = np.zeros((1, 4))
+            split.append(split[-1] + bp.shape[0])
+            out.append(bp)
+        out = np.concatenate(out, 0)[:, :3].astype(np.float32)
+        # camera -> lidar box conversion with a KITTI-like calibration
+        rect = np.eye(4, dtype=np.float32)
+        rect[:3, :3] = np.array([[0.9999, 0.0098, -0.0074], [-0.0099, 0.9999, -0.0043], [0.0074, 0.0044, 0.9999]], np.float32)
+        v2c = np.eye(4, dtype=np.float32)
+        v2c[:3, :] = np.array([[0.0075, -0.9999, -0.0006, -0.0041], [0.0148, 0.0007, -0.9998, -0.0763],
+                               [0.9998, 0.0075, 0.0148, -0.2718]], np.float32)
+        cam = np.concatenate([rng.uniform([-20, 0, 5], [20, 2, 60], size=(n, 3)), rng.uniform(1, 4, size=(n, 3)),
+                              rng.uniform(-3, 3, size=(n, 1))], 1).astype(np.float32)
+        lid = box_np_ops.box_camera_to_lidar(cam, rect, v2c)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), points=pts, boxes=boxes, out=out,
+                            split=np.asarray(split, np.int64), rect=rect, v2c=v2c, cam=cam, lidar=lid)
+        print(name, out.shape, split[-1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    crop_goldens()
     torch.set_num_threads(os.cpu_count())
     for case in CASES:
         out = reference_forward(case)
