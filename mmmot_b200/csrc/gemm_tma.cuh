@@ -225,6 +225,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
         const bool rowok = co < p.M;
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
         double d1 = 0.0, d2 = 0.0;
+        const bool pass2 = P.segsum && !p.part && !p.Y && !p.relu;
 #pragma unroll 1
         for (int cc = 0; cc < 4; cc++) {
           const int col0 = half * 128 + cc * 32;
@@ -234,6 +235,27 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           if (P.t.dbg & 1) continue;
           float s1 = 0.f, s2 = 0.f;
           bool fast = col0 + 32 <= len;
+          if (pass2 && fast) {
+            // second (recomputing) pass, whole chunk inside one detection: bias, addend and the GroupNorm affine
+            // fold into one fma per element; no statistics, nothing stored
+            const int da = __ldg(p.seg + c0 + col0);
+            if (__ldg(p.seg + c0 + col0 + 31) == da) {
+              if (rowok) {
+                const float na = __ldg(p.sc + (long)g * p.M + co), nb = __ldg(p.sh + (long)g * p.M + co);
+                float bva = bv;
+                if (p.addend) bva += __ldg(p.addend + (long)da * p.ld_add + co);
+                const float a2 = P.t.out_scale * na, b2 = fmaf(bva, na, nb);
+                float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  r0 += fmaxf(fmaf(__uint_as_float(v[j]), a2, b2), 0.f);
+                  r1 += fmaxf(fmaf(__uint_as_float(v[j + 1]), a2, b2), 0.f);
+                }
+                atomicAdd(P.segsum + (long)da * p.M + co, __float2ull_rn((r0 + r1) * 4294967296.f));
+              }
+              continue;
+            }
+          }
           float bva = bv;
           if (fast && p.addend) {
             const int da = __ldg(p.seg + c0 + col0), db = __ldg(p.seg + c0 + col0 + 31);
@@ -463,7 +485,10 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.t.Wp = Wp;
   P.t.m_tiles = (g.M + 127) / 128;
   P.t.k_chunks = g.K / tc::BK;
-  P.t.mt_per_cta = P.t.m_tiles >= 2 ? 2 : 1;
+  // two 128-row subtiles per CTA share each operand box; short K chains (<= 8 chunks) are epilogue-bound instead,
+  // so they run one subtile per tile and double-buffer the accumulator in TMEM (epilogue overlaps the next MMAs).
+  // The arithmetic of a subtile does not depend on this choice.
+  P.t.mt_per_cta = (P.t.m_tiles >= 2 && (P.t.k_chunks > 8 || (mm_debug_flags() & 16))) ? 2 : 1;
   P.t.out_scale = out_scale;
   P.t.out_mode = out_mode;
   P.t.dbg = mm_debug_flags();
