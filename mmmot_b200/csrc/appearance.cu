@@ -167,6 +167,40 @@ __global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __res
   }
 }
 
+// First VGG layer on the tensor cores: the 3-channel fp32 NCHW crop is expanded to the 27 (+5 zero) taps of every
+// pixel, k = ci*9 + ky*3 + kx, as FP16 hi/lo planes [2][pixels][32]; the layer is then a K=32 contraction on the TMA
+// engine whose epilogue writes the NHWC planes conv 1 reads.  One thread per pixel, 64 B per plane.
+__global__ void __launch_bounds__(256) im2col27_kernel(const float* __restrict__ in, long n_pix, int H, int W,
+                                                       __half* __restrict__ out, long plane) {
+  const long pix = (long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= n_pix) return;
+  const int hw = H * W;
+  const long img = pix / hw;
+  const int r = (int)(pix - img * hw);
+  const int y = r / W, x = r - y * W;
+  const float* src = in + img * 3 * hw;
+  __align__(16) __half h[32], l[32];
+#pragma unroll
+  for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(src + (long)ci * hw + yy * W + xx) : 0.f;
+        tma::split_f16(v, h[ci * 9 + ky * 3 + kx], l[ci * 9 + ky * 3 + kx]);
+      }
+#pragma unroll
+  for (int k = 27; k < 32; k++) { h[k] = __ushort_as_half(0); l[k] = __ushort_as_half(0); }
+  uint4* dh = reinterpret_cast<uint4*>(out + pix * 32);
+  uint4* dl = reinterpret_cast<uint4*>(out + plane + pix * 32);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    dh[q] = reinterpret_cast<const uint4*>(h)[q];
+    dl[q] = reinterpret_cast<const uint4*>(l)[q];
+  }
+}
+
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
   // 128 threads (4 warps)
 #pragma unroll
@@ -259,11 +293,25 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     for (int i = 0; i < 13; i++) {
       const int cout = kVggCout[i], cin = kVggCin[i];
       const long plane_out = (long)n_img * h * w * cout;
+      int pooled_in_epilogue = 0;
       if (i == 0) {
-        const long quads = (long)n_img * h * w / 2;   // pixel pairs
-        conv0_packed_kernel<<<mm_cdiv(quads, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0], quads,
-                                                               h, w, hb[which], plane_out);
-        MM_LAUNCH_CHECK();
+        const long n_pix = (long)n_img * h * w;
+        if (mm_debug_flags() & 32) {   // A/B: direct FP32 FFMA first layer
+          conv0_packed_kernel<<<mm_cdiv(n_pix / 2, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
+                                                                     n_pix / 2, h, w, hb[which], plane_out);
+          MM_LAUNCH_CHECK();
+        } else {
+          if (n_pix >= (1L << 31)) return MMMOT_E_SHAPE;
+          __half* cols = hb[which ^ 1];   // [2][pixels][32] taps, dead once the contraction has run
+          im2col27_kernel<<<mm_cdiv(n_pix, 256), 256, 0, st>>>(crops, n_pix, h, w, cols, n_pix * 32);
+          MM_LAUNCH_CHECK();
+          GemmP p = gemm_defaults();
+          p.bias = wts->w[MMMOT_W_VGG_B0]; p.M = cout; p.K = 32; p.relu = 1;
+          p.S = (int)n_pix; p.tiles_per_group = mm_cdiv(n_pix, tc::BN); p.num_tiles = p.tiles_per_group;
+          p.Y = reinterpret_cast<float*>(hb[which]); p.y_ms = cout;
+          MM_TRY(gemm_tma_launch_mat(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0], wts->tc_scale[MMMOT_W_VGG_WP0], cols,
+                                     n_pix * 32, n_pix, 32, tma::OUT_PLANAR, plane_out, st));
+        }
       } else {
         GemmP p = gemm_defaults();
         p.bias = wts->w[MMMOT_W_VGG_B0 + i];
@@ -271,18 +319,24 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
         p.relu = 1;
         const bool timed = mm_timing_on();   // roofline hook: the tcgen05 conv launches
         if (timed) mm_timing_begin(st, 2.0 * cout * 9.0 * cin * (double)n_img * h * w);
+        // a pooled layer asks for the 2x2 max-pool to be fused into the epilogue (64-channel layers can)
         MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
-                                    cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch));
+                                    cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch,
+                                    kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue));
         if (timed) mm_timing_end(st);
       }
       cur = hb[which]; cur_plane = plane_out; which ^= 1;
       if (kPoolAfter[i]) {
         h /= 2; w /= 2;
         const long plane_p = (long)n_img * h * w * cout;
-        const long n8 = plane_p / 8;
-        maxpool2_planar_kernel<<<mm_cdiv(n8, 256), 256, 0, st>>>(cur, hb[which], n8, h, w, cout, cur_plane, plane_p);
-        MM_LAUNCH_CHECK();
-        cur = hb[which]; cur_plane = plane_p; which ^= 1;
+        if (pooled_in_epilogue) {
+          cur_plane = plane_p;
+        } else {
+          const long n8 = plane_p / 8;
+          maxpool2_planar_kernel<<<mm_cdiv(n8, 256), 256, 0, st>>>(cur, hb[which], n8, h, w, cout, cur_plane, plane_p);
+          MM_LAUNCH_CHECK();
+          cur = hb[which]; cur_plane = plane_p; which ^= 1;
+        }
         int s = kSkipAfter[i];
         if (s >= 0) {
           plane_mean_planar_kernel<<<mm_cdiv((long)n_img * kSkipC[s], 128), 128, 0, st>>>(cur, pooled[s], n_img, h * w,

@@ -41,6 +41,7 @@ struct TmaP {
   long plane_elems;         // output: distance (in fp16 elements) between the hi and lo planes
   int ksegs, kc_per_seg;    // conv: K is accumulated in `ksegs` TMEM passes of kc_per_seg chunks whose fp32
   float* acc_scratch;       // partial sums are combined in fp32 RN through acc_scratch[pixel][M] (see launcher)
+  int halo, pool;           // pixel-major kernel only (gemm_tma_px.cuh): vertical taps from one halo box; fused 2x2 max-pool
   unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
 };
@@ -63,6 +64,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
          (4ull << 61);
+}
+// one 32-byte (whole sector) store; dst 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* dst, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* dst, const uint32_t* r) {
+  st_global_256(dst, make_uint4(r[0], r[1], r[2], r[3]), make_uint4(r[4], r[5], r[6], r[7]));
 }
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   unsigned short a, b;
@@ -144,28 +154,36 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
     __half* scr = reinterpret_cast<__half*>(epi_scratch + warp * T_EPI_SCRATCH);
     // final conv values x[j] (pixel column col0+j, channel cb+lane) -> FP16 hi/lo NHWC planes.  The 32x32 block is
     // transposed through smem so that lane p stores the 32 channels (64 contiguous bytes) of pixel col0+p.
-    auto store_planar_block = [&](const float (&x)[32], int col0, int cb, int i0, int y0, int x0) {
+    // lane p stores the 32 channels (64 contiguous bytes per plane) of "its" row: x[j] is (row col0+j, channel cb+lane),
+    // the 32x32 block is transposed through the warp's smem scratch; o = element offset of this lane's row at channel cb
+    auto store_rows = [&](const float (&x)[32], bool ok, long o) {
       __half h[32], l[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) split_f16(x[j], h[j], l[j]);
-      const int col = col0 + lane;
-      const int xx = col & (P.bx - 1), r = col >> lbx;
-      const int yy = r & (P.by - 1), ii = r >> lby;
-      const int img = i0 + ii, y = y0 + yy, xg = x0 + xx;
-      const bool ok = img < P.n_img && y < P.H && xg < P.W;
-      const long o = (((long)img * P.H + y) * P.W + xg) * p.y_ms + cb;
 #pragma unroll
       for (int pl = 0; pl < 2; pl++) {
 #pragma unroll
         for (int j = 0; j < 32; j++) scr[j * 40 + lane] = pl ? l[j] : h[j];
         __syncwarp();
         if (ok) {
+          // 256-bit stores: each instruction writes whole 32-byte sectors (16-byte pieces cost a partial-sector
+          // write each and ran the first layers' epilogues at ~1.8 TB/s)
           const uint4* src = reinterpret_cast<const uint4*>(scr + lane * 40);
-          uint4* dst = reinterpret_cast<uint4*>(yh + o + (pl ? P.plane_elems : 0));
-          dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+          __half* dst = yh + o + (pl ? P.plane_elems : 0);
+          const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+          st_global_256(dst, a, b);
+          st_global_256(dst + 16, c, d);
         }
         __syncwarp();
       }
+    };
+    // conv tiles: column -> (image, y, x) of the box, NHWC output
+    auto store_planar_block = [&](const float (&x)[32], int col0, int cb, int i0, int y0, int x0) {
+      const int col = col0 + lane;
+      const int xx = col & (P.bx - 1), r = col >> lbx;
+      const int yy = r & (P.by - 1), ii = r >> lby;
+      const int img = i0 + ii, y = y0 + yy, xg = x0 + xx;
+      store_rows(x, img < P.n_img && y < P.H && xg < P.W, (((long)img * P.H + y) * P.W + xg) * p.y_ms + cb);
     };
 
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -314,7 +332,12 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           } else {
             const int nvalid = min(32, len - col0);
             const long row0 = (long)g * p.y_gs + c0 + col0;
-            if (P.t.out_mode == OUT_PLANAR) {
+            if (P.t.out_mode == OUT_PLANAR && !(p.y_ms & 31)) {
+              float xv[32];
+#pragma unroll
+              for (int j = 0; j < 32; j++) xv[j] = __uint_as_float(v[j]);
+              store_rows(xv, lane < nvalid, (row0 + lane) * p.y_ms + (co - lane));
+            } else if (P.t.out_mode == OUT_PLANAR) {
               __half* dst = yh + row0 * p.y_ms + co;
 #pragma unroll
               for (int j = 0; j < 32; j++)
@@ -465,6 +488,23 @@ static inline int make_map_4d(CUtensorMap* m, const void* basep, int n_img, int 
 
 }  // namespace tma
 
+#include "gemm_tma_px.cuh"
+
+// pixel-major kernel for 64-channel planar outputs (see gemm_tma_px.cuh); P fully prepared by the caller
+static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtensorMap& ml, int sms, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tma::PX_SMEM_BYTES));
+    attr = true;
+  }
+  const long total = P.t.g.num_tiles;
+  const int grid = (int)(total < sms ? total : sms);
+  tma::gemm_tma_px_kernel<<<grid, tma::T_THREADS, tma::PX_SMEM_BYTES, st>>>(P, mh, ml);
+  MM_LAUNCH_CHECK();
+  return 0;
+}
+
 // 1x1 contraction on planar FP16 (hi, lo) channels-last activations X_hi[rows][ldx], X_lo = X_hi + x_plane.
 // g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
 static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
@@ -498,6 +538,9 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));
+  if (out_mode == tma::OUT_PLANAR && g.M == 64 && g.y_ms == 64 && !g.part && !segsum && !g.addend && !g.tile_tab &&
+      !(P.t.dbg & 64))
+    return gemm_tma_px_launch(P, mh, ml, sms, st);
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);
@@ -512,7 +555,8 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
 // accumulation error.  nullptr = single pass.
 static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                 int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st,
-                                float* acc_scratch = nullptr) {
+                                float* acc_scratch = nullptr, long y_plane_pooled = 0, int* did_pool = nullptr) {
+  if (did_pool) *did_pool = 0;
   if (!Wp || C % tc::BK) return MMMOT_E_ARG;
   static int sms = 0;
   if (!sms) {
@@ -533,11 +577,28 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
         if (waste < best - 1e-9) { best = waste; bx = cx; by = cy; bi = ci; }
       }
   }
+  // 64-channel outputs run on the pixel-major kernel (gemm_tma_px.cuh); it prefers a 16 x 16 single-image box
+  // (vertical taps from one halo box, 2x2 pooling windows inside a warp) when that wastes no more than the best box
+  const int seg_chunks = mm_kseg_chunks();   // 0 = single pass
+  const int dbg = mm_debug_flags();
+  const bool px = g0.M == 64 && !g0.part && !(dbg & 64) && !(acc_scratch && seg_chunks > 0 && 9 * C / tc::BK > seg_chunks);
+  if (px) {
+    const double best = (double)mm_cdiv(W, bx) * bx / W * mm_cdiv(H, by) * by / H * mm_cdiv(n_img, bi) * bi / n_img;
+    const double w16 = (double)mm_cdiv(W, 16) * 16 / W * mm_cdiv(H, 16) * 16 / H;
+    if (w16 <= best + 1e-9) { bx = 16; by = 16; bi = 1; }
+  }
   tma::TmaP P;
   memset(&P, 0, sizeof(P));
   GemmP g = g0;
   g.K = 9 * C;
   P.conv = 1; P.bx = bx; P.by = by; P.bi = bi;
+  if (px) {
+    P.halo = (bi == 1 && bx >= 8 && bx * (by + 2) * 64 <= tma::PX_X_PLANE && !(dbg & 256)) ? 1 : 0;
+    if (y_plane_pooled > 0 && did_pool && bx >= 2 && bx <= 16 && by >= 2 && !(H & 1) && !(W & 1) && !(dbg & 512)) {
+      P.pool = 1;
+      *did_pool = 1;
+    }
+  }
   P.tiles_x = mm_cdiv(W, bx); P.tiles_y = mm_cdiv(H, by);
   P.n_img = n_img; P.H = H; P.W = W; P.C = C;
   g.num_tiles = P.tiles_x * P.tiles_y * mm_cdiv(n_img, bi);
@@ -552,17 +613,18 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
   P.t.out_scale = out_scale;
   P.t.out_mode = tma::OUT_PLANAR;
   P.t.dbg = mm_debug_flags();
-  P.plane_elems = y_plane;
+  P.plane_elems = P.pool ? y_plane_pooled : y_plane;
   P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
-  const int seg_chunks = mm_kseg_chunks();   // 0 = single pass
   if (acc_scratch && seg_chunks > 0 && P.t.k_chunks > seg_chunks) {
     P.ksegs = (P.t.k_chunks + seg_chunks - 1) / seg_chunks;
     P.kc_per_seg = (P.t.k_chunks + P.ksegs - 1) / P.ksegs;
     P.acc_scratch = acc_scratch;
   }
   alignas(64) CUtensorMap mh, ml;
-  MM_TRY(tma::make_map_4d(&mh, Xhi, n_img, H, W, C, bx, by, bi));
-  MM_TRY(tma::make_map_4d(&ml, Xhi + x_plane, n_img, H, W, C, bx, by, bi));
+  const int box_y = P.halo ? by + 2 : by;
+  MM_TRY(tma::make_map_4d(&mh, Xhi, n_img, H, W, C, bx, box_y, bi));
+  MM_TRY(tma::make_map_4d(&ml, Xhi + x_plane, n_img, H, W, C, bx, box_y, bi));
+  if (px) return gemm_tma_px_launch(P, mh, ml, sms, st);
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);
