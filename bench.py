@@ -75,7 +75,9 @@ class ClockSampler(threading.Thread):
         mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        pw = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit())
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def pick_cpu_threads():
@@ -285,7 +287,11 @@ def main():
         sampler.start()
     ms, launches, hook = timed(step_resident, args.steps, args.warmup, with_hooks=True)
     clocks = sampler.summary() if sampler else None
+    sampler2 = ClockSampler(local) if rank == 0 else None
+    if sampler2:
+        sampler2.start()
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
+    clocks_e2e = sampler2.summary() if sampler2 else None
 
     if rank == 0:
         peaks, how = load_peaks()
@@ -327,7 +333,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 (tcgen05 engine: FP16 hi/lo split operands, fp32 accumulate)" if args.engine != "fp32" else "f32", "data": "synthetic", "config": dict(config_dict(B, world), engine=args.engine),
-                "clocks": clocks,
+                "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "e2e": {"value": e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),

@@ -525,10 +525,10 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.t.Wp = Wp;
   P.t.m_tiles = (g.M + 127) / 128;
   P.t.k_chunks = g.K / tc::BK;
-  // two 128-row subtiles per CTA share each operand box; short K chains (<= 8 chunks) are epilogue-bound instead,
+  // two 128-row subtiles per CTA share each operand box; short K chains (<= 16 chunks) are epilogue-bound instead,
   // so they run one subtile per tile and double-buffer the accumulator in TMEM (epilogue overlaps the next MMAs).
   // The arithmetic of a subtile does not depend on this choice.
-  P.t.mt_per_cta = (P.t.m_tiles >= 2 && (P.t.k_chunks > 8 || (mm_debug_flags() & 16))) ? 2 : 1;
+  P.t.mt_per_cta = (P.t.m_tiles >= 2 && (P.t.k_chunks > 16 || (mm_debug_flags() & 16))) ? 2 : 1;
   P.t.out_scale = out_scale;
   P.t.out_mode = out_mode;
   P.t.dbg = mm_debug_flags();
