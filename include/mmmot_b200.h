@@ -190,6 +190,23 @@ int mmmot_crop_scatter(const float* points, int n_points, int stride, const floa
                        const int* split, int out_channels, float* out_points, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/*
+ * Per-detection image crop-and-resize (SURVEY.md 8f row N2 — the image-side step right before the hot path).
+ * Replaces reference dataset/test_seq_dataset.py:212-218 (PIL crop + 224x224 BILINEAR resize per detection) and
+ * utils/build_util.py:137-142 (ToTensor + Normalize): image uint8 [img_h][img_w][3] (device), boxes int32
+ * [n_det][4] = (x1, y1, x2, y2) integer crop boxes (floor/ceil of the detection boxes, taken on the host like the
+ * reference; may reach outside the image: PIL pads with 0), row_off int64 [n_det + 1] = prefix sum of the crop
+ * heights (y2 - y1), total_rows = row_off[n_det], max_crop_h = largest crop height, mean_std = 6 host floats
+ * (mean r,g,b then std r,g,b).  out fp32 [n_det][3][out_size][out_size], bit-identical to the reference's PIL +
+ * torchvision result (Pillow 8-bit two-pass resampler reproduced in fixed point).  taps = the filter-tap stride:
+ * max over boxes and axes of ceil(max(crop side / out_size, 1)) * 2 + 1, at most mmmot_crop_resize_max_taps().
+ */
+int mmmot_crop_resize_max_taps(void);
+size_t mmmot_crop_resize_workspace(int n_det, long total_rows, int out_size, int taps);
+int mmmot_crop_resize(const unsigned char* image, int img_h, int img_w, const int* boxes, const long long* row_off,
+                      int n_det, long total_rows, int max_crop_h, int out_size, int taps, const float* mean_std,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Contraction engine selection: 0 = auto (tcgen05 tensor-core engine for large problems, FP32 FFMA
  * engine for tiny ones), 1 = force the FP32 FFMA engine, 2 = force the tcgen05 engine.  Both engines
  * implement the same contraction; the switch exists for A/B parity tests and profiling. */

@@ -86,9 +86,44 @@ def crop_goldens():
         print(name, out.shape, split[-1])
 
 
+def resize_goldens():
+    """Image crop-and-resize with the reference's own calls: PIL crop + BILINEAR resize
+    (dataset/test_seq_dataset.py:212-218) and the evaluation transform of utils/build_util.py:137-142.  The frame is
+    regenerated from tests.helpers.synthetic_image; stored: float outputs at 32x32 for every box, sha256 of the
+    224x224 float outputs, and two full 224x224 uint8 crops."""
+    import hashlib
+    import numpy as np
+    import torchvision.transforms as transforms
+    from PIL import Image
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    from helpers import RESIZE_BOXES, synthetic_image
+    img = Image.fromarray(synthetic_image(), "RGB")
+    normalize = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    store = {"boxes": np.asarray(RESIZE_BOXES, np.float64)}
+    for S in (224, 32):
+        tf = transforms.Compose([transforms.Resize(S), transforms.CenterCrop(S), transforms.ToTensor(), normalize])
+        outs, u8 = [], []
+        for b in RESIZE_BOXES:
+            x1, y1, x2, y2 = np.floor(b[0]), np.floor(b[1]), np.ceil(b[2]), np.ceil(b[3])
+            crop = img.crop((x1, y1, x2, y2)).resize((S, S), Image.BILINEAR)
+            u8.append(np.asarray(crop))
+            outs.append(tf(crop).unsqueeze(0))
+        outs = torch.cat(outs, 0).numpy()
+        if S == 32:
+            store["out32"] = outs
+        else:
+            store["sha224"] = np.asarray([hashlib.sha256(o.tobytes()).hexdigest() for o in outs])
+            store["u8_224_first"] = u8[0]
+            store["u8_224_full"] = u8[9]
+    np.savez_compressed(os.path.join(OUT, "resize_kitti.npz"), **store)
+    print("resize_kitti", store["out32"].shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     crop_goldens()
+    resize_goldens()
     torch.set_num_threads(os.cpu_count())
     for case in CASES:
         out = reference_forward(case)

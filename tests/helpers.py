@@ -38,3 +38,29 @@ def det_close(a, ref, thr, tol):
     un = lambda s: torch.where(s < 0, s + 1, s)
     a, ref = un(a.detach().cpu().double()), un(ref.detach().cpu().double())
     return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)) <= tol
+
+
+def synthetic_image(h=375, w=1242, seed=5):
+    """Deterministic uint8 RGB test frame [h][w][3] (KITTI-sized by default): smooth structure + LCG noise, pure
+    integer numpy arithmetic so the golden script and the tests regenerate the same bytes anywhere."""
+    import numpy as np
+    y, x = np.mgrid[0:h, 0:w].astype(np.int64)
+    img = np.empty((h, w, 3), np.uint8)
+    state = (x * 1103515245 + y * 12345 + seed * 2654435761) & 0x7FFFFFFF
+    for c in range(3):
+        state = (state * 1103515245 + 12345 + c) & 0x7FFFFFFF
+        smooth = ((x * (3 + c)) // 7 + (y * (5 - c)) // 3 + 40 * c) % 256
+        block = (((x // 16) * 37 + (y // 16) * 91 + c * 17) % 5) * 23
+        noise = (state >> 16) % 41
+        img[..., c] = np.clip((smooth * 2 + block * 2 + noise * 3) // 4, 0, 255).astype(np.uint8)
+    return img
+
+
+RESIZE_BOXES = [
+    (712.40, 143.00, 810.73, 307.92), (599.41, 156.40, 629.75, 189.25), (387.63, 181.54, 423.81, 203.12),
+    (0.00, 120.30, 180.20, 374.00), (1100.5, 150.2, 1241.0, 374.9), (-12.3, 100.0, 60.5, 260.0),
+    (500.0, 160.0, 724.0, 384.0), (300.2, 170.9, 302.9, 175.1), (10.0, 10.0, 234.0, 234.0),
+    (0.0, 0.0, 1242.0, 375.0), (640.7, 172.3, 657.1, 186.8), (800.0, -20.0, 1000.0, 150.0),
+    (222.22, 111.11, 555.55, 333.33), (900.1, 180.2, 1010.9, 250.7), (50.5, 200.5, 274.5, 300.5),
+    (1200.0, 300.0, 1260.0, 390.0),
+]
