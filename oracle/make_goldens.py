@@ -120,10 +120,49 @@ def resize_goldens():
     print("resize_kitti", store["out32"].shape)
 
 
+def stitch_goldens():
+    """Track-id assignment + stitching + KITTI text through the UNMODIFIED reference
+    tracking_model.TrackingModule.assign_det_id / align_id and utils.data_util.write_kitti_result.  Absent
+    third-party imports of those modules (ortools behind `solvers`, pyproj) are stubbed: neither is used here."""
+    import copy
+    import json
+    import sys
+    import tempfile
+    import types
+    sys.path.insert(0, ref_loader.REF)
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    sys.modules.setdefault("pyproj", types.ModuleType("pyproj"))
+    if "solvers" not in sys.modules:
+        sys.modules["solvers"] = types.SimpleNamespace(ortools_solve=None)
+    from helpers import stitch_scenario
+    import tracking_model as ref_tm
+    from utils.data_util import write_kitti_result
+    gold = {}
+    for seed in (0, 1, 2):
+        dets, samples = stitch_scenario(seed)
+        tm = ref_tm.TrackingModule(types.SimpleNamespace(test_mode=0), None, None, det_type="3D")
+        steps = []
+        for (a, b), split, a_det, a_link, a_new, a_end in samples:
+            pair = [copy.deepcopy(dets[a]), copy.deepcopy(dets[b])]
+            ids, boxes = tm.assign_det_id(a_det, a_link, a_new, a_end, split, pair)
+            local = [[int(v) for v in x] for x in ids]
+            aligned, adets, start = tm.align_id(ids, boxes)
+            steps.append({"local": local, "aligned": [[int(v) for v in x] for x in aligned], "frame_start": int(start),
+                          "frames": [int(d["frame_idx"][0]) for d in adets], "last_id": int(tm.last_id)})
+        with tempfile.TemporaryDirectory() as tmp:
+            write_kitti_result(tmp, "0000", "step", tm.frames_id, copy.deepcopy(tm.frames_det), part="val")
+            text = open(os.path.join(tmp, "step", "val", "0000.txt")).read()
+        gold[str(seed)] = {"steps": steps, "frames_id": [[int(v) for v in x] for x in tm.frames_id], "kitti": text}
+    with open(os.path.join(OUT, "stitch.json"), "w") as f:
+        json.dump(gold, f)
+    print("stitch", {k: len(v["steps"]) for k, v in gold.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     crop_goldens()
     resize_goldens()
+    stitch_goldens()
     torch.set_num_threads(os.cpu_count())
     for case in CASES:
         out = reference_forward(case)

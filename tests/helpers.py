@@ -64,3 +64,59 @@ RESIZE_BOXES = [
     (222.22, 111.11, 555.55, 333.33), (900.1, 180.2, 1010.9, 250.7), (50.5, 200.5, 274.5, 300.5),
     (1200.0, 300.0, 1260.0, 390.0),
 ]
+
+
+def stitch_scenario(seed=0, frames=8):
+    """Synthetic evaluation sequence for the id-stitching tests: per-frame detection dicts in the
+    DataLoader layout of the reference (leading batch dimension 1) and, for every consecutive frame pair, a feasible
+    set of assignment matrices (kept flags, one-to-one links, new/end flags).  Covers: dropped detections, births,
+    deaths, a frame without kept detections, a kept set that differs between the two samples sharing a frame, and a
+    break in the frame numbering.  Returns (dets per frame, list of samples); a sample is
+    (frame ids (a, b), det_split, assign_det, [assign_link 1 x na x nb], assign_new, assign_end)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    counts = [int(c) for c in rng.integers(3, 7, size=frames)]
+    frame_no = list(range(frames))
+    for t in range(frames // 2 + 1, frames):
+        frame_no[t] += 5                                   # numbering break inside the sequence
+    dets = []
+    for t, n in enumerate(counts):
+        bbox = rng.uniform(0, 300, size=(n, 4)).astype(np.float32)
+        dets.append({
+            "name": torch.from_numpy(rng.integers(0, 4, size=(1, n))).long(),
+            "truncated": torch.from_numpy(rng.uniform(0, 1, size=(1, n)).astype(np.float32)),
+            "occluded": torch.from_numpy(rng.integers(0, 3, size=(1, n))).long(),
+            "alpha": torch.from_numpy(rng.uniform(-3, 3, size=(1, n)).astype(np.float32)),
+            "bbox": torch.from_numpy(bbox[None]),
+            "dimensions": torch.from_numpy(rng.uniform(1, 4, size=(1, n, 3)).astype(np.float32)),
+            "location": torch.from_numpy(rng.uniform(-20, 40, size=(1, n, 3)).astype(np.float32)),
+            "rotation_y": torch.from_numpy(rng.uniform(-3, 3, size=(1, n)).astype(np.float32)),
+            "frame_idx": torch.tensor([frame_no[t]]),
+        })
+    keep = [rng.uniform(size=n) < 0.8 for n in counts]
+    keep[3][:] = False                                     # a frame where nothing is kept
+    samples = []
+    for a in range(frames - 1):
+        b = a + 1
+        if frame_no[b] != frame_no[a] + 1:
+            continue                                       # the sequence is cut here: no sample spans the break
+        ka, kb = keep[a].copy(), keep[b].copy()
+        if a == 1:
+            ka[np.flatnonzero(~ka)[:1]] = True             # this sample keeps one more detection of frame a than the last
+        na, nb = counts[a], counts[b]
+        link = np.zeros((na, nb), np.float32)
+        new = np.zeros(na + nb, np.float32)
+        end = np.zeros(na + nb, np.float32)
+        free = list(rng.permutation(np.flatnonzero(ka)))
+        for j in np.flatnonzero(kb):
+            if free and rng.uniform() < 0.7:
+                link[free.pop(), j] = 1
+            else:
+                new[na + j] = 1
+        for k in np.flatnonzero(ka):
+            if link[k].sum() == 0:
+                end[k] = 1
+        assign_det = np.concatenate([ka, kb]).astype(np.float32)
+        samples.append(((a, b), [torch.tensor([na]), torch.tensor([nb])], torch.from_numpy(assign_det),
+                        [torch.from_numpy(link[None])], torch.from_numpy(new), torch.from_numpy(end)))
+    return dets, samples
