@@ -244,10 +244,35 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
         double d1 = 0.0, d2 = 0.0;
         const bool pass2 = P.segsum && !p.part && !p.Y && !p.relu;
+        // Everything the four 32-column chunks need from global memory is fetched up front, so its latency is paid once
+        // per subtile instead of once (or twice, seg -> addend) per chunk: the detection index at both ends of every
+        // chunk (one load: lane 2c / 2c+1 holds chunk c's first / last column), the per-detection addend row of every
+        // single-detection chunk, and the GroupNorm affine of the recomputing pass.
+        const bool use_seg = p.seg && (p.addend || P.segsum);
+        int segv = 0;
+        if (use_seg && lane < 8) {
+          const int col = min(half * 128 + (lane >> 1) * 32 + ((lane & 1) ? 31 : 0), len - 1);
+          if (col >= 0) segv = __ldg(p.seg + c0 + col);
+        }
+        float adv[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned one_det = 0;   // bit c: chunk c is complete and lies inside one detection
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int da = __shfl_sync(0xffffffffu, segv, 2 * c), db = __shfl_sync(0xffffffffu, segv, 2 * c + 1);
+          if (use_seg && half * 128 + c * 32 + 32 <= len && da == db) {
+            one_det |= 1u << c;
+            if (p.addend && rowok) adv[c] = __ldg(p.addend + (long)da * p.ld_add + co);
+          }
+        }
+        float na = 0.f, nb = 0.f;
+        if (P.segsum && rowok) { na = __ldg(p.sc + (long)g * p.M + co); nb = __ldg(p.sh + (long)g * p.M + co); }
 #pragma unroll 1
         for (int cc = 0; cc < 4; cc++) {
           const int col0 = half * 128 + cc * 32;
           if (col0 >= len) break;   // warp-uniform
+          const int da = __shfl_sync(0xffffffffu, segv, 2 * cc);
+          const float adc = cc == 0 ? adv[0] : cc == 1 ? adv[1] : cc == 2 ? adv[2] : adv[3];
+          const bool single = (one_det >> cc) & 1u;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(mt * 256 + col0), v);
           if (P.t.dbg & 1) continue;
@@ -256,12 +281,9 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           if (pass2 && fast) {
             // second (recomputing) pass, whole chunk inside one detection: bias, addend and the GroupNorm affine
             // fold into one fma per element; no statistics, nothing stored
-            const int da = __ldg(p.seg + c0 + col0);
-            if (__ldg(p.seg + c0 + col0 + 31) == da) {
+            if (single) {
               if (rowok) {
-                const float na = __ldg(p.sc + (long)g * p.M + co), nb = __ldg(p.sh + (long)g * p.M + co);
-                float bva = bv;
-                if (p.addend) bva += __ldg(p.addend + (long)da * p.ld_add + co);
+                const float bva = bv + adc;
                 const float a2 = P.t.out_scale * na, b2 = fmaf(bva, na, nb);
                 float r0 = 0.f, r1 = 0.f;
 #pragma unroll
@@ -276,8 +298,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           }
           float bva = bv;
           if (fast && p.addend) {
-            const int da = __ldg(p.seg + c0 + col0), db = __ldg(p.seg + c0 + col0 + 31);
-            if (da == db) { if (rowok) bva += __ldg(p.addend + (long)da * p.ld_add + co); }
+            if (single) bva += adc;
             else fast = false;
           }
           if (fast) {
@@ -300,11 +321,10 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
             // GroupNorm + ReLU + per-detection sum fused into the (recomputing) second pass: the activation never
             // reaches HBM.  Run sums are fp32 in column order; runs are merged with integer atomics, so the result
             // does not depend on the order in which tiles finish.
-            const float na = __ldg(p.sc + (long)g * p.M + co), nb = __ldg(p.sh + (long)g * p.M + co);
             const int nvalid = min(32, len - col0);
-            int dcur = __ldg(p.seg + c0 + col0);
+            int dcur = da;
             float run = 0.f;
-            if (nvalid == 32 && __ldg(p.seg + c0 + col0 + 31) == dcur) {
+            if (single) {
               // common case: the whole 32-column chunk belongs to one detection
 #pragma unroll
               for (int j = 0; j < 32; j++) run += fmaxf(fmaf(__uint_as_float(v[j]), na, nb), 0.f);
@@ -349,9 +369,14 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
                 }
             } else {   // OUT_CL fp32 channels-last
               float* dst = p.Y + row0 * p.y_ms + co;
+              if (nvalid == 32) {
 #pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (j < nvalid) dst[(long)j * p.y_ms] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; j++) { *dst = __uint_as_float(v[j]); dst += p.y_ms; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                  if (j < nvalid) dst[(long)j * p.y_ms] = __uint_as_float(v[j]);
+              }
             }
           }
         }
