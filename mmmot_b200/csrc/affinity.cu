@@ -49,28 +49,33 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
 }
 
 // ---- channels-last (tensor-core path) variants: y[(g*N + i)*M + j][ld] ----
-// end_vec[c][i] = mean_j relu(GN(y0))   -> V[c][g*(M+N) + M + i];  one CTA per (g, i), threads over channels
-__global__ void end_mean_cl_kernel(const float* __restrict__ y, long ld, int coff, const float* __restrict__ sc,
-                                   const float* __restrict__ sh, int N, int M, long ldv, float* __restrict__ V) {
-  const int g = blockIdx.x / N, i = blockIdx.x % N;
-  const float* src = y + ((long)(g * N + i) * M) * ld + coff;
+// end_vec[c][i] = mean_j relu(GN(y0)) -> V[c][g*(M+N) + M + i]   (CTA r < N of group g: row i = r, sum over j)
+// new_vec[c][j] = mean_i relu(GN(y0)) -> V[c][g*(M+N) + j]       (CTA r >= N: column j = r - N, sum over i)
+// One launch, grid = G x (N + M) with a group's CTAs adjacent: the row pass and the column pass of a group run
+// together, so the group's 2 KB-per-row slab is read from HBM once and the second use hits L2.  Threads over channels
+// (coalesced 1 KB per row), 8 independent loads in flight per thread, fixed summation order.
+__global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __restrict__ y, long ld, int coff,
+                                                             const float* __restrict__ sc, const float* __restrict__ sh,
+                                                             int N, int M, long ldv, float* __restrict__ V) {
+  const int g = blockIdx.x / (N + M), r = blockIdx.x % (N + M);
+  const bool is_end = r < N;
+  const int cnt = is_end ? M : N;
+  const long step = is_end ? ld : (long)M * ld;
+  const float* src = y + (is_end ? (long)(g * N + r) * M : (long)g * N * M + (r - N)) * ld + coff;
   for (int c = threadIdx.x; c < 512; c += blockDim.x) {
     const float a = sc[g * 512 + c], b = sh[g * 512 + c];
+    const float* p = src + c;
     float acc = 0.f;
-    for (int j = 0; j < M; j++) acc += fmaxf(fmaf(src[(long)j * ld + c], a, b), 0.f);
-    V[(long)c * ldv + (long)g * (M + N) + M + i] = acc / (float)M;
-  }
-}
-// new_vec[c][j] = mean_i relu(GN(y0))   -> V[c][g*(M+N) + j];  one CTA per (g, j)
-__global__ void new_mean_cl_kernel(const float* __restrict__ y, long ld, int coff, const float* __restrict__ sc,
-                                   const float* __restrict__ sh, int N, int M, long ldv, float* __restrict__ V) {
-  const int g = blockIdx.x / M, j = blockIdx.x % M;
-  const float* src = y + ((long)g * N * M + j) * ld + coff;
-  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
-    const float a = sc[g * 512 + c], b = sh[g * 512 + c];
-    float acc = 0.f;
-    for (int i = 0; i < N; i++) acc += fmaxf(fmaf(src[(long)i * M * ld + c], a, b), 0.f);
-    V[(long)c * ldv + (long)g * (M + N) + j] = acc / (float)N;
+    int k = 0;
+    for (; k + 8 <= cnt; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldg(p + (long)(k + u) * step);
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc += fmaxf(fmaf(v[u], a, b), 0.f);
+    }
+    for (; k < cnt; k++) acc += fmaxf(fmaf(__ldg(p + (long)k * step), a, b), 0.f);
+    V[(long)c * ldv + (long)g * (M + N) + (is_end ? M + r : r - N)] = acc / (float)cnt;
   }
 }
 // z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : 8 lanes per row (4 float4 each), fixed-order shuffle tree
@@ -301,9 +306,7 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   // ---- new / end indicator on y0 = rows 512..1023 of y01 ----
   const long ldv = (long)G * (n + m);
   if (use_tc) {
-    end_mean_cl_kernel<<<G * n, 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
-    MM_LAUNCH_CHECK();
-    new_mean_cl_kernel<<<G * m, 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
+    newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
     MM_LAUNCH_CHECK();
   } else {
     rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,

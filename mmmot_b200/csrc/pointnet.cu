@@ -21,6 +21,59 @@ __global__ void transpose_points_kernel(const float* __restrict__ pts, float* __
   xt[2 * P + p] = pts[p * 3 + 2];
 }
 
+// First trunk layer (3 -> 64) on the tensor-core path.  With K = 3 a contraction kernel is all epilogue, so the
+// layer is never materialised in fp32: one kernel accumulates its GroupNorm statistics, a second recomputes it,
+// applies GroupNorm + ReLU and writes the FP16 hi/lo planes layer 2's TMA loads read.  Both evaluate
+//   y = fma(w2, z, fma(w1, y, fma(w0, x, b)))  in this order, so the statistics describe exactly the values normalised.
+// pts [P][3], wt [3][64], part[(tile*2 + h)*64 + c] (h = first / second half of the tile's points, fp64 sums).
+__global__ void __launch_bounds__(256) pn_l1_stats_kernel(const float* __restrict__ pts, const int4* __restrict__ tiles,
+                                                          const float* __restrict__ wt, const float* __restrict__ bias,
+                                                          double2* __restrict__ part) {
+  __shared__ float sp[256 * 3];
+  __shared__ double2 red[4][64];
+  const int4 tt = tiles[blockIdx.x];          // (pair, first point, length <= 256, -)
+  for (int i = threadIdx.x; i < tt.z * 3; i += 256) sp[i] = pts[(long)tt.y * 3 + i];
+  __syncthreads();
+  const int c = threadIdx.x & 63, qd = threadIdx.x >> 6;
+  const float w0 = wt[c], w1 = wt[64 + c], w2 = wt[128 + c], b = bias[c];
+  double s1 = 0.0, s2 = 0.0;
+  const int p1 = min(tt.z, (qd + 1) * 64);
+  for (int p = qd * 64; p < p1; p++) {
+    const float y = fmaf(w2, sp[3 * p + 2], fmaf(w1, sp[3 * p + 1], fmaf(w0, sp[3 * p], b)));
+    s1 += (double)y;
+    s2 += (double)y * (double)y;
+  }
+  red[qd][c] = make_double2(s1, s2);
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int h = threadIdx.x >> 6;
+    const double2 a = red[2 * h][c], d = red[2 * h + 1][c];
+    part[((long)blockIdx.x * 2 + h) * 64 + c] = make_double2(a.x + d.x, a.y + d.y);
+  }
+}
+// x1p planes [2][P][64] = split(relu(GN(y)))  ;  thread = (point, 4 channels)
+__global__ void __launch_bounds__(256) pn_l1_apply_kernel(const float* __restrict__ pts, const float* __restrict__ wt,
+                                                          const float* __restrict__ bias, const float* __restrict__ sc,
+                                                          const float* __restrict__ sh, const int* __restrict__ seg,
+                                                          int L, long P, __half* __restrict__ out) {
+  const long idx = (long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= P * 16) return;
+  const long row = idx >> 4;
+  const int c = (int)(idx & 15) * 4;
+  const int g = seg[row] / L;
+  const float x = __ldg(pts + row * 3), y = __ldg(pts + row * 3 + 1), z = __ldg(pts + row * 3 + 2);
+  const float4 w0 = *reinterpret_cast<const float4*>(wt + c), w1 = *reinterpret_cast<const float4*>(wt + 64 + c),
+               w2 = *reinterpret_cast<const float4*>(wt + 128 + c), b = *reinterpret_cast<const float4*>(bias + c);
+  const float4 a = *reinterpret_cast<const float4*>(sc + (long)g * 64 + c);
+  const float4 s = *reinterpret_cast<const float4*>(sh + (long)g * 64 + c);
+  float4 r;
+  r.x = fmaxf(fmaf(fmaf(w2.x, z, fmaf(w1.x, y, fmaf(w0.x, x, b.x))), a.x, s.x), 0.f);
+  r.y = fmaxf(fmaf(fmaf(w2.y, z, fmaf(w1.y, y, fmaf(w0.y, x, b.y))), a.y, s.y), 0.f);
+  r.z = fmaxf(fmaf(fmaf(w2.z, z, fmaf(w1.z, y, fmaf(w0.z, x, b.z))), a.z, s.z), 0.f);
+  r.w = fmaxf(fmaf(fmaf(w2.w, z, fmaf(w1.w, y, fmaf(w0.w, x, b.w))), a.w, s.w), 0.f);
+  split4_store(r, out + row * 64 + c, out + P * 64 + row * 64 + c);
+}
+
 // seg[p] = detection owning point p (binary search in the CSR offsets)
 __global__ void point_segment_kernel(const int* __restrict__ split, int ndet, long P, int* __restrict__ seg) {
   long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,14 +245,22 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
       const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
       if (i == 0) {
-        p.X = w.xt; p.x_ks = P;                                 // fp32 [3][P] gather
-        MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st, tc::OUT_CL));
+        if (mm_debug_flags() & 2048) {                          // A/B: first layer as a thread-fed tcgen05 contraction
+          p.X = w.xt; p.x_ks = P;                               // fp32 [3][P] gather
+          MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st, tc::OUT_CL));
+        } else {
+          pn_l1_stats_kernel<<<(int)tiles.size(), 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
+          MM_LAUNCH_CHECK();
+        }
       } else {                                                  // FP16 hi/lo planes [2][P][cin] via TMA
         MM_TRY(gemm_tma_launch_mat(p, wp, wps, i == 1 ? w.x1p : w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st));
       }
       MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
-      if (i < 4) {
+      if (i == 0 && !(mm_debug_flags() & 2048)) {
+        pn_l1_apply_kernel<<<mm_cdiv(P * 16, 256), 256, 0, st>>>(points, q[0], q[1], w.sc, w.sh, w.seg, L, P, w.x1p);
+        MM_LAUNCH_CHECK();
+      } else if (i < 4) {
         MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, st));
       } else {
         // second pass of the 1024-wide layer: recompute, GroupNorm + ReLU + per-detection mean in the epilogue
