@@ -303,15 +303,15 @@ def main():
         tc_engine = args.engine != "fp32"
         traffic = None
         try:    # dram bytes per frame-pair of the 12 conv launches, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01_conv3s_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
                 tr = json.load(f)
             if tc_engine:
                 traffic = tr["dram_bytes_per_pair"] * (B / max(conv_n / (12 * args.steps), 1)) / 12
         except Exception:
             pass
         roofline = {"bound": "tensor",
-                    "kernel": ("tma::gemm_tma_kernel, conv mode (TMA-fed tcgen05 3x3-conv contraction of the VGG trunk, FP16 "
-                               "hi/lo split: 3 MMAs per algorithmic MAC)") if tc_engine else
+                    "kernel": ("tma::gemm_tma_kernel / gemm_tma_px_kernel, conv mode (TMA-fed tcgen05 3x3-conv contraction of the VGG "
+                               "trunk, layers 1..12, FP16 hi/lo split: 3 MMAs per algorithmic MAC)") if tc_engine else
                               "gemm_simt_kernel<XM_CONV3> (VGG 3x3 conv contraction, FP32 FFMA engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "mma_issue_tflops": 3 * achieved if tc_engine else None,
@@ -320,7 +320,7 @@ def main():
                                    "ALGORITHMIC FLOPs (2*Cout*9Cin*pixels per launch); the tensor pipe executes 3x that",
                     "launches_timed": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
                     "share_of_step": conv_ms / ms, "traffic": traffic,
-                    "traffic_note": "avg dram bytes per launch, scaled from profiles/r01_conv3s_traffic.json"}
+                    "traffic_note": "avg dram bytes per launch, scaled from profiles/r01_conv_traffic.json (ncu --set full)"}
         cpu = None
         if not args.no_cpu:
             threads = pick_cpu_threads()
