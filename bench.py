@@ -322,7 +322,7 @@ def main():
                     "share_of_step": conv_ms / ms, "traffic": traffic,
                     "traffic_note": "avg dram bytes per launch, scaled from profiles/r01_conv_traffic.json (ncu --set full)"}
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU baseline is reported at N=1 only
             threads = pick_cpu_threads()
             rate, secs = oracle_pairs_per_s(args.cpu_pairs, threads)
             cpu = {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
