@@ -205,3 +205,23 @@ def test_predict_batch_full_size_property():
     al, ad = o["assign_link"][0], o["assign_det"][0]
     assert al.sum(1).max() <= 1 and al.sum(0).max() <= 1
     assert torch.equal(o["assign_end"][0][:n] + al.sum(1), ad[:n])
+
+
+def test_cfg4_full_size_pair_matches_oracle():
+    """One frame-pair at exactly the bench configuration (BASELINE configs[1] / cfg4: Fusion C, minus_abs, dual_add,
+    N=M=128, P=512 points per detection, 64x64 crops) against the oracle — the size the throughput is quoted on.
+    The oracle needs ~10 s of host time for this pair."""
+    net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 4)
+    n = 128
+    dets, info, split = synthetic_pair(n, n, 512, 64, seed=123)
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    ref_det, ref_link, ref_new, ref_end, _ = torch_ref.forward(sd, dets, info, split, "C", "minus_abs", "dual_add", 0.2)
+    det, link, new, end, _ = net(dets.cuda(), {k: v.cuda() for k, v in info.items()}, split)
+    assert relerr(link[0], ref_link[0]) < TOL
+    assert relerr(new, ref_new) < TOL and relerr(end, ref_end) < TOL
+    assert det_close(det, ref_det, 0.2, TOL)
+    # and the assignment computed from both score sets agrees wherever the LP optimum is unambiguous
+    a = mmmot_b200.ortools_solve(det[2], [link[0][2:3]], new[2], end[2], split)
+    b = mmmot_b200.ortools_solve(ref_det[2].cuda(), [ref_link[0][2:3].cuda()], ref_new[2].cuda(), ref_end[2].cuda(), split)
+    agree = (a[1][0] == b[1][0]).float().mean().item()
+    assert agree > 0.999, agree
