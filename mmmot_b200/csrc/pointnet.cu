@@ -118,22 +118,6 @@ __global__ void pointnet_out_kernel(const float* __restrict__ O, const float* __
   feats[(((long)pair * 3 + 1) * 512 + c) * L + l] = v;
 }
 
-// channels-last variant: Y[p][C]; one CTA per detection, threads over channels (coalesced), points in order
-// -> out[c][d] (channel-major, consumed by the FP32 engine's small contractions).
-__global__ void segment_mean_cl_kernel(const float* __restrict__ Y, int C, const int* __restrict__ split,
-                                       const float* __restrict__ sc, const float* __restrict__ sh, int ndet,
-                                       int L, float* __restrict__ out) {
-  const int d = blockIdx.x;
-  const int pair = d / L;
-  const int s = split[d], e = split[d + 1];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float a = sc[(long)pair * C + c], b = sh[(long)pair * C + c];
-    float acc = 0.f;
-    for (int p = s; p < e; p++) acc += fmaxf(fmaf(Y[(long)p * C + c], a, b), 0.f);
-    out[(long)c * ndet + d] = e > s ? acc / (float)(e - s) : 0.f;
-  }
-}
-
 // out[c][d] = segsum[d][c] * 2^-32 / (points of detection d)   (fixed-point sums of the fused segment-sum epilogue)
 __global__ void segsum_mean_kernel(const unsigned long long* __restrict__ segsum, const int* __restrict__ split,
                                    int C, int ndet, float* __restrict__ out) {
@@ -155,14 +139,15 @@ struct PnWs {
   int4* tiles;
 };
 
-PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
+// use_tc: the tensor-core path never materialises the 1024-wide activation (537 MB per frame-pair at cfg4)
+PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles, bool use_tc) {
   PnWs w;
   long nd = (long)pairs * L;
   w.xt = a.take<float>(3 * P);
   w.y1 = a.take<float>(64 * P);
   w.t0 = a.take<float>(128 * P);
   w.t1 = a.take<float>(64 * P);
-  w.big = a.take<float>(1024 * P);
+  w.big = a.take<float>(use_tc ? 0 : 1024 * P);
   w.segsum = a.take<unsigned long long>(1024 * nd);
   w.x1p = a.take<__half>(2 * 64 * P);
   w.xp = a.take<__half>(2 * 128 * P);
@@ -186,9 +171,12 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles) {
 
 }  // namespace
 
+// engine choice from the per-pair shape only (see appearance.cu)
+static bool pointnet_use_tc(int L) { return mm_engine() == 2 || (mm_engine() == 0 && L >= 16); }
+
 extern "C" size_t mmmot_pointnet_workspace(int pairs, int L, long p_total) {
   MmArena a(nullptr, 0);
-  carve(a, pairs, L, p_total, p_total / 128 + 2 * pairs + 2);
+  carve(a, pairs, L, p_total, p_total / 128 + 2 * pairs + 2, pointnet_use_tc(L));
   return a.off;
 }
 
@@ -205,7 +193,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     if (h_det_split[d + 1] <= h_det_split[d]) return MMMOT_E_SHAPE;  // every detection owns >= 1 point
 
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
-  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && L >= 16);   // per-pair shape only (see appearance.cu)
+  const bool use_tc = pointnet_use_tc(L);
   const int TNW = use_tc ? tc::BN : 128;
   std::vector<int4> tiles;
   std::vector<int> cnt(pairs), gstart(pairs + 1);
@@ -218,7 +206,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   gstart[pairs] = (int)tiles.size();
   const long max_tiles = P / 128 + 2 * pairs + 2;   // also bounds 2 partials per 256-wide tile
   MmArena ar(workspace, workspace_bytes);
-  PnWs w = carve(ar, pairs, L, P, max_tiles);
+  PnWs w = carve(ar, pairs, L, P, max_tiles, use_tc);
   if (!ar.ok() || (long)tiles.size() > max_tiles) return MMMOT_E_WORKSPACE;
   MM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(w.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
