@@ -214,12 +214,22 @@ int mmmot_set_engine(int engine);
 
 /* Accuracy / speed knob of the tcgen05 conv engine.  The tensor core's fp32 accumulator rounds toward zero at
  * every K=16 step (bias ~ steps * 2^-25), so K chains longer than `chunks` x 32 are accumulated in several
- * TMEM passes whose partial sums are added in fp32 round-to-nearest.  0 = single pass (fastest),
- * 72 (default) splits only the K = 4608 layers, 36 also the K = 2304 layers. */
+ * TMEM passes whose partial sums are added in fp32 round-to-nearest.  0 = single pass (fastest, end-to-end link
+ * error up to 7.9e-5 on the test cases), 36 (default) splits the K >= 2304 layers (error <= 3.9e-5; bound 1e-4),
+ * 72 only the K = 4608 layers (6.8e-5). */
 int mmmot_set_kseg(int chunks);
 
-/* Profiling experiments on the tcgen05 engine (bit 0 skip epilogue work, 1 skip weight loads, 2 skip
- * operand generation, 3 skip MMA issue); results are WRONG with any bit set.  Default 0. */
+/* Profiling / A-B experiments (tools/stage_times.py, TC_DBG=...).  Results are WRONG with any of bits 0-3 set;
+ * the other bits select an alternative implementation of the same arithmetic.  Default 0.
+ *   bit 0 (1)    skip epilogue work          bit 1 (2)   skip weight loads
+ *   bit 2 (4)    skip operand loads          bit 3 (8)   skip MMA issue
+ *   bit 4 (16)   two 128-row subtiles per tile also for short K chains (no TMEM double buffering)
+ *   bit 5 (32)   first VGG layer as the direct FP32 FFMA kernel instead of im2col + tensor cores
+ *   bit 6 (64)   64-channel layers on the channel-major kernel instead of the pixel-major one
+ *   bit 7 (128)  pixel-major epilogue with 128-bit instead of 256-bit stores
+ *   bit 8 (256)  pixel-major kernel without halo boxes (nine boxes per channel chunk)
+ *   bit 9 (512)  no fused max-pool in the pixel-major epilogue
+ *   bit 11 (2048) first PointNet layer as a thread-fed tcgen05 contraction instead of the recompute kernels */
 int mmmot_set_debug(int flags);
 
 /* Test hook: Y[M][S] = W X + bias through one engine (1 = FP32 FFMA, 2 = tcgen05); Wt is [K][M] fp32,

@@ -39,7 +39,14 @@ def test_workspace_queries_need_no_gpu(lib_built):
     lib = _lib.load()
     assert lib.mmmot_appearance_workspace(16, 64, 64) > 16 * 64 * 64 * 64 * 4
     assert lib.mmmot_affinity_workspace(1, 128, 128) > 3 * 1024 * 128 * 128 * 4
-    assert lib.mmmot_pointnet_workspace(1, 16, 4096) > 1024 * 4096 * 4
+    # tensor-core path (L >= 16): fp32 trunk activations + FP16 hi/lo planes, but never the 1024-wide layer
+    tc_ws = lib.mmmot_pointnet_workspace(1, 16, 4096)
+    assert (64 + 128 + 64) * 4096 * 4 < tc_ws < 1024 * 4096 * 4
+    lib.mmmot_set_engine(1)                              # FP32 engine materialises it
+    try:
+        assert lib.mmmot_pointnet_workspace(1, 16, 4096) > 1024 * 4096 * 4
+    finally:
+        lib.mmmot_set_engine(0)
     assert lib.mmmot_fusion_det_workspace(2, 16) > 0 and lib.mmmot_lp_workspace(4, 8, 8) > 0
     # argument validation happens before any CUDA call
     assert lib.mmmot_lp_assign(None, 0, None, 0, None, 0, None, 0, 1, 1, 1, None, None, None, None, None, None, 0, None) == -1
