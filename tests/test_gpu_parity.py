@@ -208,7 +208,7 @@ def test_predict_batch_full_size_property():
 
 
 def test_cfg4_full_size_pair_matches_oracle():
-    """One frame-pair at exactly the bench configuration (BASELINE configs[1] / cfg4: Fusion C, minus_abs, dual_add,
+    """One frame-pair at exactly the bench configuration (BASELINE configs[3] / SURVEY cfg4: Fusion C, minus_abs, dual_add,
     N=M=128, P=512 points per detection, 64x64 crops) against the oracle — the size the throughput is quoted on.
     The oracle needs ~10 s of host time for this pair."""
     net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 4)
