@@ -12,6 +12,8 @@
  *   - no allocation, no ownership transfer, stateless, stream-ordered (last argument is a
  *     cudaStream_t passed as void*), thread-safe across streams.
  *   - return 0 on success, a negative MMMOT_E_* on a bad argument, or a positive cudaError_t.
+ *   - every `workspace` starts with a 256-byte STATUS BLOCK (included in the mmmot_*_workspace sizes): stages raise
+ *     flags in it while they run and never clear it.  Protocol: mmmot_status_reset(ws) -> stages ... -> mmmot_status_check(ws).
  *   - all real data is fp32; `stats` scratch is fp64.
  *   - "group" = one GroupNorm domain.  A frame-pair with N previous / M next detections has
  *     L = N + M detections; all pairs of one call share N, M, crop size H x W.
@@ -28,12 +30,14 @@
 extern "C" {
 #endif
 
-#define MMMOT_ABI_VERSION 1
+#define MMMOT_ABI_VERSION 2
 
 enum {
   MMMOT_E_ARG = -1,        /* null pointer / non-positive size / unsupported enum */
   MMMOT_E_WORKSPACE = -2,  /* workspace too small */
-  MMMOT_E_SHAPE = -3       /* shape constraint violated (see function comment) */
+  MMMOT_E_SHAPE = -3,      /* shape constraint violated (see function comment) */
+  MMMOT_E_RANGE = -4       /* an activation left FP16's range (|x| >= 65504) on the tensor-core path: the result
+                              of the stage that raised it is clamped, i.e. WRONG (mmmot_status_check) */
 };
 
 /* fusion_module_{A,B,C}: reference modules/fusion_net.py:73,45,6 */
@@ -101,6 +105,12 @@ typedef struct mmmot_weights {
 } mmmot_weights;
 
 int mmmot_abi_version(void);
+
+/* Status block of a workspace (see Conventions).  reset: stream-ordered clear.  check: copies the status word back,
+ * SYNCHRONISES the stream and returns 0 or MMMOT_E_RANGE.  The tensor-core engines feed activations to the MMA units
+ * as FP16 hi/lo pairs; a value with |x| >= 65504 saturates in that conversion, which these calls make loud. */
+int mmmot_status_reset(void* workspace, void* stream);
+int mmmot_status_check(const void* workspace, void* stream);
 /* number of SMs / name of the current device: lets the host fail loudly when no sm_100 GPU is present */
 int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -133,10 +143,13 @@ int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points, const int*
  * Fusion A/B/C -> stack 2 of feats, then the detection-score branch on all 3 stacks.
  * Replaces fusion_module_{A,B,C}.forward (modules/fusion_net.py:31-42,62-70,85-92) and
  * TrackingNet.determine_det eval branch (modules/tracking_net.py:149-163).
- *   det_scores [pairs][3][L]   = sigmoid(w_det(feats)) - [. < neg_threshold]
+ *   det_scores [pairs][3][L]   = s - [s < neg_threshold],  s = sigmoid(w_det(feats)) if score_flags & MMMOT_SCORE_SIGMOID
+ *                                ('cls' in score_arch, tracking_net.py:153-156) else w_det(feats);
+ *                                the threshold step is skipped without MMMOT_SCORE_THRESHOLD.
  */
+enum { MMMOT_SCORE_SIGMOID = 1, MMMOT_SCORE_THRESHOLD = 2 };
 size_t mmmot_fusion_det_workspace(int pairs, int L);
-int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, float neg_threshold,
+int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, int score_flags, float neg_threshold,
                          int pairs, int L, float* feats, float* det_scores,
                          void* workspace, size_t workspace_bytes, void* stream);
 
@@ -144,7 +157,9 @@ int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, float neg_th
  * Pairwise affinity + start/end indicator + softmax mode.
  * Replaces affinity_module.forward (modules/gcn.py:68-82), NewEndIndicator_v2.forward
  * (modules/new_end.py:62-82, mode 'avg') and TrackingNet.associate (tracking_net.py:106-126).
- * The 3 x 512 x N x M pairwise tensor is generated tile by tile and never stored.
+ * The 3 x 512 x N x M pairwise tensor is generated tile by tile inside the first contraction's operand producers
+ * (csrc/gemm_gen.cuh) and never stored; GroupNorm + ReLU between the MLP layers is applied by the next layer's
+ * producers, so each layer output crosses HBM once as fp32.
  *   link  [pairs][3][N][M]
  *   new_s [pairs][3][M]   end_s [pairs][3][N]   (un-padded; the host pads with zeros as
  *                                                tracking_net.py:183-189 does)
@@ -228,14 +243,19 @@ int mmmot_set_kseg(int chunks);
  *   bit 6 (64)   64-channel layers on the channel-major kernel instead of the pixel-major one
  *   bit 7 (128)  pixel-major epilogue with 128-bit instead of 256-bit stores
  *   bit 8 (256)  pixel-major kernel without halo boxes (nine boxes per channel chunk)
- *   bit 9 (512)  no fused max-pool in the pixel-major epilogue
- *   bit 11 (2048) first PointNet layer as a thread-fed tcgen05 contraction instead of the recompute kernels */
+ *   bit 9 (512)  no fused max-pool in the pixel-major epilogue */
 int mmmot_set_debug(int flags);
 
-/* Test hook: Y[M][S] = W X + bias through one engine (1 = FP32 FFMA, 2 = tcgen05); Wt is [K][M] fp32,
- * Wp the packed FP16 hi/lo tiles of the same matrix (wp_scale = its 2^-s), X is [K][S], all device pointers. */
+/* Test hook: Y[M][S] = W X + bias through the FP32 FFMA engine (engine must be 1); Wt is [K][M] fp32, X is [K][S],
+ * all device pointers (Wp / wp_scale are ignored; the tcgen05 engines have the planar / gen hooks below). */
 int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const float* bias, const float* X,
                        float* Y, int M, int K, int S, int engine, void* stream);
+
+/* Test hook of the generated-operand tcgen05 engine (csrc/gemm_gen.cuh, GroupNorm+ReLU producer): with X [S][K] and
+ * Y [S][M] fp32 channels-last, Y = relu(X*sc + sh) W^T + bias, sc/sh [K] per input channel (K a multiple of 32,
+ * <= 512).  Wp = packed FP16 hi/lo tiles of W [M][K]. */
+int mmmot_debug_linear_gen(const void* Wp, float wp_scale, const float* bias, const float* X, const float* sc,
+                           const float* sh, float* Y, int M, int K, int S, void* stream);
 
 /* Test hooks of the TMA-fed tcgen05 engine: operands are two FP16 planes (hi, lo), channels-last.
  * linear: Y[rows][M] fp32 = X W^T + bias, X planes [2][rows][K].  conv: 3x3 pad 1 + bias + ReLU on NHWC planes
@@ -246,11 +266,16 @@ int mmmot_debug_conv_planar(const void* Wp, float wp_scale, const float* bias, c
                             int n_img, int H, int W, int C, int M, float* kseg_scratch /* fp32 [n*H*W][M] or NULL */,
                             void* stream);
 
-/* Per-launch timing of the dominant kernel (3x3-conv contraction of the VGG trunk) with CUDA events
- * on the launching stream; used by bench.py's roofline figure.  collect() returns the summed
- * duration (ms), the summed algorithmic FLOPs (2*Cout*9Cin*pixels) and the launch count of every
- * timed launch since the last collect(). */
+/* Per-launch timing of the hot kernels with CUDA events on the launching stream; used by bench.py's roofline
+ * figures.  Every timed launch carries a tag = (stage, layer) — mmmot_timing_tag_count() tags, named by
+ * mmmot_timing_tag_name() — and its ALGORITHMIC work (FLOPs; compulsory HBM bytes of that launch).
+ * collect_tags() fills arrays of tag_count entries (any may be NULL) with the summed duration (ms), FLOPs, bytes and
+ * launch count per tag since the last collect; collect() returns the totals over the 3x3-conv contractions of the
+ * VGG trunk (layers 1..12, FLOPs = 2*Cout*9Cin*pixels), the dominant kernels. */
 int mmmot_timing_enable(int on);
+int mmmot_timing_tag_count(void);
+const char* mmmot_timing_tag_name(int tag);
+int mmmot_timing_collect_tags(double* ms, double* flop, double* bytes, long* launches);
 int mmmot_timing_collect(double* total_ms, double* total_flop, long* launches);
 
 /* counts kernel launches made through this library since process start (bench.py gpu_launches) */

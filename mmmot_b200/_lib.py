@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmmot_sm100a.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mmmot_b200.h")
 
+ABI_VERSION = 2
+SCORE_SIGMOID, SCORE_THRESHOLD = 1, 2
 FUSION = {"A": 0, "B": 1, "C": 2}
 AFFINITY = {"multiply": 0, "minus_abs": 1, "minus": 2}
 SOFTMAX = {"none": 0, "single": 1, "dual": 2, "dual_add": 3, "dual_max": 4}
@@ -54,13 +56,19 @@ SIGNATURES = {
     "mmmot_debug_linear_planar": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _l, _vp]),
     "mmmot_debug_conv_planar": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmmot_timing_enable": (_i, [_i]),
+    "mmmot_timing_tag_count": (_i, []),
+    "mmmot_timing_tag_name": (ctypes.c_char_p, [_i]),
+    "mmmot_timing_collect_tags": (_i, [ctypes.POINTER(ctypes.c_double)] * 3 + [ctypes.POINTER(ctypes.c_long)]),
+    "mmmot_status_reset": (_i, [_vp, _vp]),
+    "mmmot_status_check": (_i, [_vp, _vp]),
+    "mmmot_debug_linear_gen": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),
     "mmmot_appearance_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmmot_pointnet_workspace": (_sz, [_i, _i, _l]),
     "mmmot_pointnet_fwd": (_i, [_wp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "mmmot_fusion_det_workspace": (_sz, [_i, _i]),
-    "mmmot_fusion_det_fwd": (_i, [_wp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_fusion_det_fwd": (_i, [_wp, _i, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_affinity_workspace": (_sz, [_i, _i, _i]),
     "mmmot_affinity_fwd": (_i, [_wp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_crop_workspace": (_sz, [_i, _i]),
@@ -98,7 +106,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mmmot_abi_version() != 1:
+    if lib.mmmot_abi_version() != ABI_VERSION:
         raise MmmotError("ABI version mismatch between mmmot_b200/_lib.py and libmmmot_sm100a.so")
     _lib = lib
     return lib
@@ -107,6 +115,8 @@ def load():
 def check(code, what):
     if code == 0:
         return
-    names = {-1: "MMMOT_E_ARG", -2: "MMMOT_E_WORKSPACE", -3: "MMMOT_E_SHAPE"}
+    names = {-1: "MMMOT_E_ARG", -2: "MMMOT_E_WORKSPACE", -3: "MMMOT_E_SHAPE",
+             -4: "MMMOT_E_RANGE (an activation reached |x| >= 65504, FP16's range, on the tensor-core path; the outputs are "
+                 "clamped and must not be used — run with mmmot_b200.set_engine('fp32') for such checkpoints)"}
     msg = names.get(code, f"cudaError {code}" if code > 0 else str(code))
     raise MmmotError(f"{what} failed: {msg}")

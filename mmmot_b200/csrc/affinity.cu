@@ -3,10 +3,14 @@
 // (NewEndIndicator_v2.forward, mode 'avg') and modules/tracking_net.py:106-126 (associate).
 //
 // Groups g = pair*3 + stack.  The pairwise tensor x[g][c][i][j] (reference gcn.py:13,24-27;
-// 100.7 MB per pair at N=M=128) is generated inside the first contraction's operand loader and
+// 100.7 MB per pair at N=M=128) is generated inside the first contraction's operand producers and
 // never exists in HBM; affinity conv1.0 and new/end conv0 (both 512->512 on the same x) run as
-// ONE 512->1024 contraction.
+// ONE 512->1024 contraction.  On the tensor-core path (gemm_gen.cuh) the GroupNorm + ReLU between
+// the MLP layers is applied by the next contraction's producers while they build its operand, so
+// each layer output crosses HBM once as channels-last fp32 (written by one epilogue, read by the
+// next layer's producers).
 #include "norm_ops.cuh"
+#include "gemm_gen.cuh"
 #include "tc_ops.cuh"
 
 namespace {
@@ -202,7 +206,6 @@ __global__ void softmax_apply_kernel(const float* __restrict__ z, int mode, int 
 
 struct AfWs {
   float *y01, *y2, *y3, *z;
-  __half* xp;     // tensor-core path: FP16 hi/lo operand planes [2][G*NM][512]
   float* fcl;     // tensor-core path: channels-last copy of the feature stacks [G][L][512]
   float *sc1, *sh1, *sc0, *sh0, *sc2, *sh2, *sc3, *sh3;
   float *v, *h1, *h2, *nsc1, *nsh1, *nsc2, *nsh2;
@@ -219,7 +222,6 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.y2 = a.take<float>(G * 512 * NM);
   w.y3 = a.take<float>(G * 128 * NM);
   w.z = a.take<float>(G * NM);
-  w.xp = a.take<__half>(2 * G * NM * 512);
   w.fcl = a.take<float>(G * (n + m) * 512);
   w.sc1 = a.take<float>(G * 512); w.sh1 = a.take<float>(G * 512);
   w.sc0 = a.take<float>(G * 512); w.sh0 = a.take<float>(G * 512);
@@ -238,6 +240,12 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.part = a.take<double2>(G * 2 * mm_cdiv(NM, 256) * 1024);   // covers 1 partial per 128-tile and 2 per 256-tile
   w.npart = a.take<double2>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);
   return w;
+}
+
+template <int GEN>
+int launch_gen(const GemmP& p, const mmmot_weights* wts, int wid, const float* src, int src_m, const float* gsc,
+               const float* gsh, int n, int m, int Lf, int* status, cudaStream_t st) {
+  return gemm_gen_launch<GEN>(p, (const uint4*)wts->w[wid], wts->tc_scale[wid], src, src_m, gsc, gsh, n, m, Lf, status, st);
 }
 
 }  // namespace
@@ -263,28 +271,26 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && NM >= 256);   // per-pair shape only (see appearance.cu)
   const int tpg = mm_cdiv(NM, use_tc ? tc::BN : 128);
   const float* const* W = wts->w;
+  const bool timed = mm_timing_on();
 
   // layer 1: [conv1.0 ; w_new_end.conv0] 512 -> 1024 on the generated pairwise tensor.
   // FP32 engine: y01[g][1024][NM].  Tensor-core engine: channels-last y01[g*NM + s][1024].
   const int pm = use_tc ? 2 : 1;   // GroupNorm partials per column tile
   if (use_tc) {
-    // pairwise operand emitted once as packed FP16 words (coalesced float4 in / uint4 out), then a plain
-    // packed-operand contraction
-    const long rows = (long)G * NM;
     MM_TRY(transpose_f32(feats, w.fcl, 512, L, G, st));
-    const int nb = mm_cdiv(rows * 128, 256);
-    if (affinity_op == MMMOT_AFF_MULTIPLY) pair_split_kernel<MMMOT_AFF_MULTIPLY><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
-    else if (affinity_op == MMMOT_AFF_MINUS_ABS) pair_split_kernel<MMMOT_AFF_MINUS_ABS><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
-    else pair_split_kernel<MMMOT_AFF_MINUS><<<nb, 256, 0, st>>>(w.fcl, n, m, rows, w.xp);
-    MM_LAUNCH_CHECK();
     GemmP p = gemm_defaults();
     p.bias = W[MMMOT_W_AF_B01]; p.M = 1024; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
-    p.x_gs = NM;
     p.Y = w.y01; p.y_gs = NM; p.y_ms = 1024;
     p.part = w.part;
-    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W01P], wts->tc_scale[MMMOT_W_AF_W01P], w.xp, rows * 512,
-                               rows, 512, tc::OUT_CL, 0, st));
+    if (timed) mm_timing_begin(st, MM_T_AFF_L1, 2.0 * 1024 * 512 * (double)G * NM, 4.0 * 1024 * (double)G * NM);
+    int r = affinity_op == MMMOT_AFF_MULTIPLY
+                ? launch_gen<gen::GEN_PAIR_MUL>(p, wts, MMMOT_W_AF_W01P, w.fcl, 0, nullptr, nullptr, n, m, L, ar.status(), st)
+            : affinity_op == MMMOT_AFF_MINUS_ABS
+                ? launch_gen<gen::GEN_PAIR_ABS>(p, wts, MMMOT_W_AF_W01P, w.fcl, 0, nullptr, nullptr, n, m, L, ar.status(), st)
+                : launch_gen<gen::GEN_PAIR_SUB>(p, wts, MMMOT_W_AF_W01P, w.fcl, 0, nullptr, nullptr, n, m, L, ar.status(), st);
+    if (r) return r;
+    if (timed) mm_timing_end(st);
   } else {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_AF_W01T]; p.bias = W[MMMOT_W_AF_B01]; p.ldw = 1024; p.M = 1024; p.K = 512;
@@ -303,11 +309,13 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G1W], W[MMMOT_W_AF_G1B], nullptr, NM, G, 512, 1, w.sc1, w.sh1, st, 1024, 0));
   MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G0W], W[MMMOT_W_AF_G0B], nullptr, NM, G, 512, 512, w.sc0, w.sh0, st, 1024, 512));
 
-  // ---- new / end indicator on y0 = rows 512..1023 of y01 ----
+  // ---- new / end indicator on y0 = channels 512..1023 of y01 ----
   const long ldv = (long)G * (n + m);
   if (use_tc) {
+    if (timed) mm_timing_begin(st, MM_T_AFF_MEAN, 0.0, 4.0 * 512 * (double)G * NM);
     newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
     MM_LAUNCH_CHECK();
+    if (timed) mm_timing_end(st);
   } else {
     rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
                                                                n, m, ldv, w.v);
@@ -339,24 +347,23 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
 
   // ---- affinity MLP layers 2, 3 on y1 = channels 0..511 of y01 ----
   if (use_tc) {
-    // GroupNorm+ReLU applied once per element by norm_split -> packed FP16 operand of the next contraction
-    const long rows = (long)G * NM;
-    MM_TRY(norm_split(w.y01, 1024, w.sc1, w.sh1, 512, rows, NM, nullptr, 0, w.xp, st));
+    // GroupNorm + ReLU of the previous layer is applied by this layer's operand producers (gemm_gen.cuh, GEN_NORM)
     GemmP p = gemm_defaults();
     p.bias = W[MMMOT_W_AF_B2]; p.M = 512; p.K = 512;
     p.S = NM; p.tiles_per_group = tpg; p.num_tiles = tpg * G;
     p.x_gs = NM;
     p.Y = w.y2; p.y_gs = NM; p.y_ms = 512;
     p.part = w.part;
-    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W2P], wts->tc_scale[MMMOT_W_AF_W2P], w.xp, rows * 512, rows,
-                               512, tc::OUT_CL, 0, st));
+    if (timed) mm_timing_begin(st, MM_T_AFF_L2, 2.0 * 512 * 512 * (double)G * NM, 4.0 * (512 + 512) * (double)G * NM);
+    MM_TRY(launch_gen<gen::GEN_NORM>(p, wts, MMMOT_W_AF_W2P, w.y01, 1024, w.sc1, w.sh1, 0, 0, 0, ar.status(), st));
+    if (timed) mm_timing_end(st);
     MM_TRY(stats_reduce(w.part, 512, G, tpg, nullptr, w.stats, st, 2));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G2W], W[MMMOT_W_AF_G2B], nullptr, NM, G, 512, 1, w.sc2, w.sh2, st));
-    MM_TRY(norm_split(w.y2, 512, w.sc2, w.sh2, 512, rows, NM, nullptr, 0, w.xp, st));
     p.bias = W[MMMOT_W_AF_B3]; p.M = 128;
     p.Y = w.y3; p.y_ms = 128;
-    MM_TRY(gemm_tma_launch_mat(p, (const uint4*)W[MMMOT_W_AF_W3P], wts->tc_scale[MMMOT_W_AF_W3P], w.xp, rows * 512, rows,
-                               512, tc::OUT_CL, 0, st));
+    if (timed) mm_timing_begin(st, MM_T_AFF_L3, 2.0 * 128 * 512 * (double)G * NM, 4.0 * (512 + 128) * (double)G * NM);
+    MM_TRY(launch_gen<gen::GEN_NORM>(p, wts, MMMOT_W_AF_W3P, w.y2, 512, w.sc2, w.sh2, 0, 0, 0, ar.status(), st));
+    if (timed) mm_timing_end(st);
     MM_TRY(stats_reduce(w.part, 128, G, tpg, nullptr, w.stats, st, 2));
     MM_TRY(gn_finalize(w.stats, W[MMMOT_W_AF_G3W], W[MMMOT_W_AF_G3B], nullptr, NM, G, 128, 1, w.sc3, w.sh3, st));
   } else {
@@ -378,6 +385,7 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   }
   float* zdst = softmax_mode == MMMOT_SM_NONE ? link : w.z;
   if (use_tc) {
+    if (timed) mm_timing_begin(st, MM_T_AFF_LOGIT, 2.0 * 128 * (double)G * NM, 4.0 * 129 * (double)G * NM);
     link_logit_cl_kernel<<<mm_cdiv((long)G * NM * 8, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
                                                                         W[MMMOT_W_AF_B4], (long)G * NM, NM, zdst);
   } else {
@@ -385,6 +393,7 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
                                                                  W[MMMOT_W_AF_B4], G, NM, zdst);
   }
   MM_LAUNCH_CHECK();
+  if (use_tc && timed) mm_timing_end(st);
   if (softmax_mode != MMMOT_SM_NONE) {
     softmax_stats_kernel<<<mm_cdiv((long)G * (n + m) * 32, 256), 256, 0, st>>>(w.z, G, n, m, w.rmax, w.rsum,
                                                                               w.cmax, w.csum);

@@ -11,6 +11,34 @@ extern "C" unsigned long long mmmot_launch_count(void) { return g_launches.load(
 
 extern "C" int mmmot_abi_version(void) { return MMMOT_ABI_VERSION; }
 
+int mm_sm_count(int* sms) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  MM_CUDA(cudaGetDevice(&dev));
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (!v) {
+    MM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return 0;
+}
+
+// ---- status block (first MM_STATUS_BYTES of every workspace) ----
+extern "C" int mmmot_status_reset(void* workspace, void* stream) {
+  if (!workspace) return MMMOT_E_ARG;
+  MM_CUDA(cudaMemsetAsync(workspace, 0, MM_STATUS_BYTES, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int mmmot_status_check(const void* workspace, void* stream) {
+  if (!workspace) return MMMOT_E_ARG;
+  int word = 0;
+  MM_CUDA(cudaMemcpyAsync(&word, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return (word & 1) ? MMMOT_E_RANGE : 0;
+}
+
 extern "C" int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   MM_CUDA(cudaGetDevice(&dev));
@@ -23,27 +51,35 @@ extern "C" int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Optional per-launch timing of the dominant kernel (the 3x3-conv contraction), used by bench.py
-// for the roofline figure: CUDA events recorded on the launching stream around every launch
-// while enabled; mmmot_timing_collect() synchronises on the events and returns the totals.
+// Optional per-launch timing of the hot kernels, used by bench.py for the roofline figures: CUDA events recorded on
+// the launching stream around every tagged launch while enabled; mmmot_timing_collect*() synchronises on the
+// events and returns the totals (per tag = per (stage, layer)).
 #include <mutex>
 #include <vector>
 
 namespace {
 std::mutex g_tmu;
 bool g_timing = false;
-struct Span { cudaEvent_t a, b; double flop; };
+struct Span { cudaEvent_t a, b; int tag; double flop, bytes; };
 std::vector<Span> g_spans;
+const char* const kTagNames[MM_T_COUNT] = {
+    "vgg.conv0", "vgg.conv1", "vgg.conv2", "vgg.conv3", "vgg.conv4", "vgg.conv5", "vgg.conv6", "vgg.conv7", "vgg.conv8",
+    "vgg.conv9", "vgg.conv10", "vgg.conv11", "vgg.conv12", "vgg.pool_mean_heads",
+    "pointnet.l1_3to64", "pointnet.l2_64to64", "pointnet.l3_64to64", "pointnet.l4_64to128", "pointnet.norm_split",
+    "pointnet.l5_128to1024_stats", "pointnet.l5_128to1024_segsum", "pointnet.head_64to512_stats",
+    "pointnet.head_64to512_segsum",
+    "affinity.l1_pair_512to1024", "affinity.newend_means", "affinity.l2_512to512", "affinity.l3_512to128",
+    "affinity.logit", "lp.assign"};
 }  // namespace
 
 bool mm_timing_on() { return g_timing; }
 
-void mm_timing_begin(cudaStream_t st, double flop) {
+void mm_timing_begin(cudaStream_t st, int tag, double flop, double bytes) {
   std::lock_guard<std::mutex> l(g_tmu);
   Span s;
   cudaEventCreate(&s.a);
   cudaEventCreate(&s.b);
-  s.flop = flop;
+  s.tag = tag; s.flop = flop; s.bytes = bytes;
   cudaEventRecord(s.a, st);
   g_spans.push_back(s);
 }
@@ -59,29 +95,55 @@ extern "C" int mmmot_timing_enable(int on) {
   return 0;
 }
 
-extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* launches) {
+extern "C" int mmmot_timing_tag_count(void) { return MM_T_COUNT; }
+extern "C" const char* mmmot_timing_tag_name(int tag) { return (tag >= 0 && tag < MM_T_COUNT) ? kTagNames[tag] : ""; }
+
+// ms / flop / bytes / launches: arrays of mmmot_timing_tag_count() entries (any may be null)
+extern "C" int mmmot_timing_collect_tags(double* ms, double* flop, double* bytes, long* launches) {
   std::lock_guard<std::mutex> l(g_tmu);
-  double ms = 0.0, fl = 0.0;
-  long n = 0;
+  for (int t = 0; t < MM_T_COUNT; t++) {
+    if (ms) ms[t] = 0.0;
+    if (flop) flop[t] = 0.0;
+    if (bytes) bytes[t] = 0.0;
+    if (launches) launches[t] = 0;
+  }
+  int rc = 0;
   for (auto& s : g_spans) {
     float t = 0.f;
     cudaError_t e = cudaEventSynchronize(s.b);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.a, s.b);
-    if (e != cudaSuccess) return (int)e;
-    ms += t; fl += s.flop; n++;
+    if (e != cudaSuccess) rc = (int)e;
+    else {
+      if (ms) ms[s.tag] += t;
+      if (flop) flop[s.tag] += s.flop;
+      if (bytes) bytes[s.tag] += s.bytes;
+      if (launches) launches[s.tag] += 1;
+    }
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);
   }
   g_spans.clear();
-  if (total_ms) *total_ms = ms;
-  if (total_flop) *total_flop = fl;
-  if (launches) *launches = n;
+  return rc;
+}
+
+// totals over the 3x3-conv contractions of the VGG trunk (layers 1..12), the dominant kernels
+extern "C" int mmmot_timing_collect(double* total_ms, double* total_flop, long* launches) {
+  double ms[MM_T_COUNT], fl[MM_T_COUNT];
+  long n[MM_T_COUNT];
+  int rc = mmmot_timing_collect_tags(ms, fl, nullptr, n);
+  if (rc) return rc;
+  double a = 0.0, b = 0.0;
+  long c = 0;
+  for (int t = MM_T_VGG0 + 1; t <= MM_T_VGG0 + 12; t++) { a += ms[t]; b += fl[t]; c += n[t]; }
+  if (total_ms) *total_ms = a;
+  if (total_flop) *total_flop = b;
+  if (launches) *launches = c;
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Engine selection + single-contraction test hook.
-#include "gemm_tc.cuh"
+#include "gemm_gen.cuh"
 
 namespace { int g_engine = 0; int g_dbg = 0; int g_kseg = 36; }
 int mm_kseg_chunks() { return g_kseg; }
@@ -99,25 +161,33 @@ extern "C" int mmmot_set_engine(int engine) {
 
 extern "C" int mmmot_debug_linear(const float* Wt, const void* Wp, float wp_scale, const float* bias, const float* X,
                                   float* Y, int M, int K, int S, int engine, void* stream) {
-  if (!Wt || !X || !Y || M <= 0 || K <= 0 || S <= 0) return MMMOT_E_ARG;
+  (void)Wp; (void)wp_scale;
+  if (!Wt || !X || !Y || M <= 0 || K <= 0 || S <= 0 || engine != 1) return MMMOT_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   GemmP p = gemm_defaults();
   p.Wt = Wt; p.ldw = M; p.bias = bias; p.M = M; p.K = K;
   p.S = S;
   p.X = X; p.x_ks = S;
   p.Y = Y; p.y_ms = S;
-  if (engine == 2) {
-    p.tiles_per_group = mm_cdiv(S, tc::BN); p.num_tiles = p.tiles_per_group;
-    return gemm_tc_launch<XM_DIRECT>(p, (const uint4*)Wp, wp_scale, st);
-  }
   p.tiles_per_group = mm_cdiv(S, 128); p.num_tiles = p.tiles_per_group;
   return gemm_simt_launch<XM_DIRECT>(p, st);
 }
 
+// Generated-operand tcgen05 engine (gemm_gen.cuh, GEN_NORM): Y[S][M] = relu(X[S][K]*sc + sh) W^T + bias with X, Y
+// fp32 channels-last, sc/sh [K].
+extern "C" int mmmot_debug_linear_gen(const void* Wp, float wp_scale, const float* bias, const float* X, const float* sc,
+                                      const float* sh, float* Y, int M, int K, int S, void* stream) {
+  if (!Wp || !X || !Y || !sc || !sh || M <= 0 || K <= 0 || S <= 0) return MMMOT_E_ARG;
+  GemmP p = gemm_defaults();
+  p.bias = bias; p.M = M; p.K = K;
+  p.S = S; p.tiles_per_group = mm_cdiv(S, tc::BN); p.num_tiles = p.tiles_per_group;
+  p.x_gs = S;
+  p.Y = Y; p.y_gs = S; p.y_ms = M;
+  return gemm_gen_launch<gen::GEN_NORM>(p, (const uint4*)Wp, wp_scale, X, K, sc, sh, 0, 0, 0, nullptr, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Test hooks for the TMA-fed tcgen05 engine (planar FP16 hi/lo channels-last operands).
-#include "gemm_tma.cuh"
-
 // Y[rows][M] fp32 (channels-last) = X W^T + bias ; X given as planes Xhi[rows][K], Xlo = Xhi + rows*K
 extern "C" int mmmot_debug_linear_planar(const void* Wp, float wp_scale, const float* bias, const void* Xhi,
                                          float* Y, int M, int K, long rows, void* stream) {

@@ -101,7 +101,7 @@ __global__ void plane_mean_planar_kernel(const __half* __restrict__ in, float* _
 // CTA = 64 pixel pairs x 4 channel groups.  wt: [(ky*3+kx)*3 + ci][64] (BN folded), ReLU fused.  W % 2 == 0.
 __global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __restrict__ in, const float* __restrict__ wt,
                                                               const float* __restrict__ bias, long n_pairs, int H, int W,
-                                                              __half* __restrict__ out, long plane) {
+                                                              __half* __restrict__ out, long plane, int* status) {
   __shared__ __align__(16) float ws[27 * 64];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = wt[i];
@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __res
   for (int p = 0; p < 2; p++) {
     __half h[16], l[16];
 #pragma unroll
-    for (int c = 0; c < 16; c++) tma::split_f16(fmaxf(acc[p][c], 0.f), h[c], l[c]);
+    for (int c = 0; c < 16; c++) {
+      tma::split_f16(fmaxf(acc[p][c], 0.f), h[c], l[c]);
+      mm_range_flag(status, acc[p][c]);
+    }
     __half* dst = out + (pix0 + p) * 64 + cg;
     reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
     reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256, 4) conv0_packed_kernel(const float* __res
 // pixel, k = ci*9 + ky*3 + kx, as FP16 hi/lo planes [2][pixels][32]; the layer is then a K=32 contraction on the TMA
 // engine whose epilogue writes the NHWC planes conv 1 reads.  One thread per pixel, 64 B per plane.
 __global__ void __launch_bounds__(256) im2col27_kernel(const float* __restrict__ in, long n_pix, int H, int W,
-                                                       __half* __restrict__ out, long plane) {
+                                                       __half* __restrict__ out, long plane, int* status) {
   const long pix = (long)blockIdx.x * 256 + threadIdx.x;
   if (pix >= n_pix) return;
   const int hw = H * W;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(256) im2col27_kernel(const float* __restrict__
   const int y = r / W, x = r - y * W;
   const float* src = in + img * 3 * hw;
   __align__(16) __half h[32], l[32];
+  float amax = 0.f;
 #pragma unroll
   for (int ci = 0; ci < 3; ci++)
 #pragma unroll
@@ -189,7 +193,9 @@ __global__ void __launch_bounds__(256) im2col27_kernel(const float* __restrict__
         const int yy = y + ky - 1, xx = x + kx - 1;
         const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(src + (long)ci * hw + yy * W + xx) : 0.f;
         tma::split_f16(v, h[ci * 9 + ky * 3 + kx], l[ci * 9 + ky * 3 + kx]);
+        amax = fmaxf(amax, fabsf(v));
       }
+  mm_range_flag(status, amax);
 #pragma unroll
   for (int k = 27; k < 32; k++) { h[k] = __ushort_as_half(0); l[k] = __ushort_as_half(0); }
   uint4* dh = reinterpret_cast<uint4*>(out + pix * 32);
@@ -290,45 +296,50 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     const __half* cur = nullptr;
     long cur_plane = 0;
     int which = 0, h = H, w = W;
+    const bool timed = mm_timing_on();   // roofline hook: every launch tagged (stage, layer)
+    int* status = ar.status();
     for (int i = 0; i < 13; i++) {
       const int cout = kVggCout[i], cin = kVggCin[i];
       const long plane_out = (long)n_img * h * w * cout;
       int pooled_in_epilogue = 0;
+      // algorithmic FLOPs 2*Cout*9Cin*pixels; compulsory bytes: activation in + activation out at 4 B per element
+      // (the pooled map when the 2x2 max-pool is fused into the epilogue)
+      if (timed) mm_timing_begin(st, MM_T_VGG0 + i, 2.0 * cout * 9.0 * cin * (double)n_img * h * w,
+                                 4.0 * (double)n_img * h * w * (cin + (i == 1 ? cout / 4.0 : cout)));
       if (i == 0) {
         const long n_pix = (long)n_img * h * w;
         if (mm_debug_flags() & 32) {   // A/B: direct FP32 FFMA first layer
           conv0_packed_kernel<<<mm_cdiv(n_pix / 2, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
-                                                                     n_pix / 2, h, w, hb[which], plane_out);
+                                                                     n_pix / 2, h, w, hb[which], plane_out, status);
           MM_LAUNCH_CHECK();
         } else {
           if (n_pix >= (1L << 31)) return MMMOT_E_SHAPE;
           __half* cols = hb[which ^ 1];   // [2][pixels][32] taps, dead once the contraction has run
-          im2col27_kernel<<<mm_cdiv(n_pix, 256), 256, 0, st>>>(crops, n_pix, h, w, cols, n_pix * 32);
+          im2col27_kernel<<<mm_cdiv(n_pix, 256), 256, 0, st>>>(crops, n_pix, h, w, cols, n_pix * 32, status);
           MM_LAUNCH_CHECK();
           GemmP p = gemm_defaults();
           p.bias = wts->w[MMMOT_W_VGG_B0]; p.M = cout; p.K = 32; p.relu = 1;
           p.S = (int)n_pix; p.tiles_per_group = mm_cdiv(n_pix, tc::BN); p.num_tiles = p.tiles_per_group;
           p.Y = reinterpret_cast<float*>(hb[which]); p.y_ms = cout;
           MM_TRY(gemm_tma_launch_mat(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0], wts->tc_scale[MMMOT_W_VGG_WP0], cols,
-                                     n_pix * 32, n_pix, 32, tma::OUT_PLANAR, plane_out, st));
+                                     n_pix * 32, n_pix, 32, tma::OUT_PLANAR, plane_out, st, nullptr, status));
         }
       } else {
         GemmP p = gemm_defaults();
         p.bias = wts->w[MMMOT_W_VGG_B0 + i];
         p.M = cout;
         p.relu = 1;
-        const bool timed = mm_timing_on();   // roofline hook: the tcgen05 conv launches
-        if (timed) mm_timing_begin(st, 2.0 * cout * 9.0 * cin * (double)n_img * h * w);
         // a pooled layer asks for the 2x2 max-pool to be fused into the epilogue (64-channel layers can)
         MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
                                     cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch,
-                                    kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue));
-        if (timed) mm_timing_end(st);
+                                    kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue, status));
       }
+      if (timed) mm_timing_end(st);
       cur = hb[which]; cur_plane = plane_out; which ^= 1;
       if (kPoolAfter[i]) {
         h /= 2; w /= 2;
         const long plane_p = (long)n_img * h * w * cout;
+        if (timed) mm_timing_begin(st, MM_T_VGG_POOL, 0.0, pooled_in_epilogue ? 4.0 * plane_p : 4.0 * 5.0 * plane_p);
         if (pooled_in_epilogue) {
           cur_plane = plane_p;
         } else {
@@ -343,6 +354,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
                                                                                          kSkipC[s], cur_plane);
           MM_LAUNCH_CHECK();
         }
+        if (timed) mm_timing_end(st);
       }
     }
   } else {
@@ -364,7 +376,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     p.tiles_per_group = mm_cdiv(p.S, 128);
     p.num_tiles = p.tiles_per_group;
     const bool timed = mm_timing_on();
-    if (timed) mm_timing_begin(st, 2.0 * p.M * (double)p.K * (double)p.S);
+    if (timed) mm_timing_begin(st, MM_T_VGG0 + i, 2.0 * p.M * (double)p.K * (double)p.S, 4.0 * (double)p.S * (p.Cin + p.M));
     MM_TRY(gemm_simt_launch<XM_CONV3>(p, st));
     if (timed) mm_timing_end(st);
     cur = buf[which]; which ^= 1;

@@ -34,9 +34,10 @@ __global__ void fusion_combine_kernel(int arch, const float* __restrict__ yp, co
   feats[(((long)pair * 3 + 2) * 512 + c) * L + l] = v;
 }
 
-// det_scores[g][l] = sigmoid(w3 . h2[g][:, l] + b3) - [sigmoid < thr]   (tracking_net.py:153-162)
+// det_scores[g][l] = s - [s < thr],  s = sigmoid(a) if 'cls' in score_arch else a,  a = w3 . h2[g][:, l] + b3
+// (tracking_net.py:153-162; the threshold step is the eval branch only)
 __global__ void det_score_kernel(const float* __restrict__ h2, const float* __restrict__ w3,
-                                 const float* __restrict__ b3, float thr, int G, int L,
+                                 const float* __restrict__ b3, int flags, float thr, int G, int L,
                                  float* __restrict__ out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= G * L) return;
@@ -44,8 +45,8 @@ __global__ void det_score_kernel(const float* __restrict__ h2, const float* __re
   const float* col = h2 + (long)g * 256 * L + l;
   float a = b3[0];
   for (int c = 0; c < 256; c++) a = fmaf(w3[c], col[(long)c * L], a);
-  float s = mm_sigmoid(a);
-  out[idx] = (s < thr) ? s - 1.0f : s;
+  float s = (flags & MMMOT_SCORE_SIGMOID) ? mm_sigmoid(a) : a;
+  out[idx] = ((flags & MMMOT_SCORE_THRESHOLD) && s < thr) ? s - 1.0f : s;
 }
 
 struct FdWs {
@@ -74,7 +75,7 @@ extern "C" size_t mmmot_fusion_det_workspace(int pairs, int L) {
   return a.off;
 }
 
-extern "C" int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, float neg_threshold,
+extern "C" int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, int score_flags, float neg_threshold,
                                     int pairs, int L, float* feats, float* det_scores, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   if (!wts || !feats || !det_scores || !workspace || pairs <= 0 || L <= 0) return MMMOT_E_ARG;
@@ -133,7 +134,7 @@ extern "C" int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, f
     MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
   }
   det_score_kernel<<<mm_cdiv((long)G * L, 128), 128, 0, st>>>(w.h2, wts->w[MMMOT_W_WD_W3],
-                                                              wts->w[MMMOT_W_WD_B3], neg_threshold, G, L,
+                                                              wts->w[MMMOT_W_WD_B3], score_flags, neg_threshold, G, L,
                                                               det_scores);
   MM_LAUNCH_CHECK();
   return 0;

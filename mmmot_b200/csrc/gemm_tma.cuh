@@ -18,7 +18,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 
 namespace tma {
 
@@ -44,6 +44,7 @@ struct TmaP {
   int halo, pool;           // pixel-major kernel only (gemm_tma_px.cuh): vertical taps from one halo box; fused 2x2 max-pool
   unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
+  int* status;              // workspace status word (FP16 range flag of the planar outputs) or null
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
@@ -150,6 +151,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
     const int q = warp & 3, half = warp >> 2;
     const int lbx = 31 - __clz(max(P.bx, 1)), lby = 31 - __clz(max(P.by, 1));
     uint32_t wcount = 0;   // (tile, segment) work items processed by this CTA
+    float amax = 0.f;      // largest magnitude converted to FP16 by this thread (range guard)
     __half* yh = reinterpret_cast<__half*>(p.Y);
     __half* scr = reinterpret_cast<__half*>(epi_scratch + warp * T_EPI_SCRATCH);
     // final conv values x[j] (pixel column col0+j, channel cb+lane) -> FP16 hi/lo NHWC planes.  The 32x32 block is
@@ -159,7 +161,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
     auto store_rows = [&](const float (&x)[32], bool ok, long o) {
       __half h[32], l[32];
 #pragma unroll
-      for (int j = 0; j < 32; j++) split_f16(x[j], h[j], l[j]);
+      for (int j = 0; j < 32; j++) { split_f16(x[j], h[j], l[j]); amax = fmaxf(amax, fabsf(x[j])); }
 #pragma unroll
       for (int pl = 0; pl < 2; pl++) {
 #pragma unroll
@@ -364,6 +366,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
                 if (j < nvalid) {
                   __half h, l;
                   split_f16(__uint_as_float(v[j]), h, l);
+                  amax = fmaxf(amax, fabsf(__uint_as_float(v[j])));
                   dst[(long)j * p.y_ms] = h;
                   dst[(long)j * p.y_ms + P.plane_elems] = l;
                 }
@@ -387,6 +390,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
       if (lane == 0) mbar_arrive(tempty_bar(abuf));
       }
     }
+    mm_range_flag(P.status, amax);
   } else if (warp == T_MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
@@ -517,12 +521,8 @@ static inline int make_map_4d(CUtensorMap* m, const void* basep, int n_img, int 
 
 // pixel-major kernel for 64-channel planar outputs (see gemm_tma_px.cuh); P fully prepared by the caller
 static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtensorMap& ml, int sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tma::PX_SMEM_BYTES));
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  MM_TRY(mm_ensure_smem(tma::gemm_tma_px_kernel, tma::PX_SMEM_BYTES, attr));
   const long total = P.t.g.num_tiles;
   const int grid = (int)(total < sms ? total : sms);
   tma::gemm_tma_px_kernel<<<grid, tma::T_THREADS, tma::PX_SMEM_BYTES, st>>>(P, mh, ml);
@@ -534,16 +534,12 @@ static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtenso
 // g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
 static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                long rows, int ldx, int out_mode, long y_plane, cudaStream_t st,
-                               unsigned long long* segsum = nullptr) {
+                               unsigned long long* segsum = nullptr, int* status = nullptr) {
   if (!Wp || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    MM_CUDA(cudaGetDevice(&dev));
-    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tma::T_SMEM_BYTES));
-  }
+  int sms = 0;
+  MM_TRY(mm_sm_count(&sms));
+  static std::atomic<unsigned long long> attr{0};
+  MM_TRY(mm_ensure_smem(tma::gemm_tma_kernel, tma::T_SMEM_BYTES, attr));
   tma::TmaP P;
   memset(&P, 0, sizeof(P));
   P.t.g = g;
@@ -560,6 +556,7 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.plane_elems = y_plane;
   P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
   P.segsum = segsum;
+  P.status = status;
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));
@@ -580,17 +577,14 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
 // accumulation error.  nullptr = single pass.
 static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                 int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st,
-                                float* acc_scratch = nullptr, long y_plane_pooled = 0, int* did_pool = nullptr) {
+                                float* acc_scratch = nullptr, long y_plane_pooled = 0, int* did_pool = nullptr,
+                                int* status = nullptr) {
   if (did_pool) *did_pool = 0;
   if (!Wp || C % tc::BK) return MMMOT_E_ARG;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    MM_CUDA(cudaGetDevice(&dev));
-    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MM_CUDA(cudaFuncSetAttribute(tma::gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tma::T_SMEM_BYTES));
-  }
+  int sms = 0;
+  MM_TRY(mm_sm_count(&sms));
+  static std::atomic<unsigned long long> attr{0};
+  MM_TRY(mm_ensure_smem(tma::gemm_tma_kernel, tma::T_SMEM_BYTES, attr));
   // box of 256 pixels = bx * by * bi (powers of two): the shape with the least padding waste, widest first
   int bx = 1, by = 1, bi = 256;
   {
@@ -639,6 +633,7 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
   P.t.out_mode = tma::OUT_PLANAR;
   P.t.dbg = mm_debug_flags();
   P.plane_elems = P.pool ? y_plane_pooled : y_plane;
+  P.status = status;
   P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
   if (acc_scratch && seg_chunks > 0 && P.t.k_chunks > seg_chunks) {
     P.ksegs = (P.t.k_chunks + seg_chunks - 1) / seg_chunks;

@@ -84,7 +84,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
     const int q = warp & 3, cb = (warp >> 2) * 32;   // TMEM lane quadrant (pixels), channel half
     const int lbx = 31 - __clz(max(P.bx, 1)), lby = 31 - __clz(max(P.by, 1));
     __half* yh = reinterpret_cast<__half*>(p.Y);
-    uint32_t wcount = 0;
+    uint32_t wcount = 0, racc = 0;   // racc: running max of the converted |hi| values (FP16 range guard)
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x, wcount++) {
       const int nt = (int)t;
       int i0 = 0, y0 = 0, x0 = 0;
@@ -134,6 +134,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
           float x1v = fmaf(__uint_as_float(v[j + 1]), P.t.out_scale, s_bias[cb + j + 1]);
           if (p.relu) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
           split_f16x2(x0v, x1v, hi[j >> 1], lo[j >> 1]);
+          mm_range_track2(racc, hi[j >> 1]);
         }
         if (ok && !(P.t.dbg & 128)) {
           // 256-bit stores: every instruction writes whole 32-byte sectors (two per plane per thread)
@@ -155,6 +156,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(abuf));
     }
+    mm_range_flag2(P.status, racc);
   } else if (warp == T_MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lp_assign_kernel(
         if (cur < mv) { mv = cur; minv[j] = cur; way[j] = j0; }
         if (mv < best) { best = mv; bj = j; }   // ascending j per lane: first minimum kept
       }
+      // the scan above wrote minv[j] / way[j] from lane (j-1)%32; the update below touches minv[j] from lane j%32
+      __syncwarp();
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
         double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -166,11 +168,14 @@ extern "C" int mmmot_lp_assign(const float* det, long det_stride, const float* l
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = lp_warp_bytes(n, m) * kWarpsPerCta;
   if (smem > 227 * 1024) return MMMOT_E_SHAPE;
-  MM_CUDA(cudaFuncSetAttribute(lp_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MM_CUDA(cudaFuncSetAttribute(lp_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // size varies: set per call
   MM_CUDA(cudaMemsetAsync(a_link, 0, (size_t)pairs * n * m * sizeof(float), st));
+  const bool timed = mm_timing_on();
+  if (timed) mm_timing_begin(st, MM_T_LP, 0.0, 4.0 * pairs * ((double)n * m * 2 + 7.0 * (n + m)));
   lp_assign_kernel<<<mm_cdiv(pairs, kWarpsPerCta), kWarpsPerCta * 32, smem, st>>>(
       det, det_stride, link, link_stride, new_s, new_stride, end_s, end_stride, pairs, n, m, a_det, a_link,
       a_new, a_end, match);
   MM_LAUNCH_CHECK();
+  if (timed) mm_timing_end(st);
   return 0;
 }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) pn_l1_stats_kernel(const float* __restric
 __global__ void __launch_bounds__(256) pn_l1_apply_kernel(const float* __restrict__ pts, const float* __restrict__ wt,
                                                           const float* __restrict__ bias, const float* __restrict__ sc,
                                                           const float* __restrict__ sh, const int* __restrict__ seg,
-                                                          int L, long P, __half* __restrict__ out) {
+                                                          int L, long P, __half* __restrict__ out, int* status) {
   const long idx = (long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= P * 16) return;
   const long row = idx >> 4;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) pn_l1_apply_kernel(const float* __restric
   r.y = fmaxf(fmaf(fmaf(w2.y, z, fmaf(w1.y, y, fmaf(w0.y, x, b.y))), a.y, s.y), 0.f);
   r.z = fmaxf(fmaf(fmaf(w2.z, z, fmaf(w1.z, y, fmaf(w0.z, x, b.z))), a.z, s.z), 0.f);
   r.w = fmaxf(fmaf(fmaf(w2.w, z, fmaf(w1.w, y, fmaf(w0.w, x, b.w))), a.w, s.w), 0.f);
-  split4_store(r, out + row * 64 + c, out + P * 64 + row * 64 + c);
+  split4_store(r, out + row * 64 + c, out + P * 64 + row * 64 + c, status);
 }
 
 // seg[p] = detection owning point p (binary search in the CSR offsets)
@@ -218,6 +218,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   MM_LAUNCH_CHECK();
 
   const int cin[5] = {3, 64, 64, 64, 128}, cout[5] = {64, 64, 64, 128, 1024};
+  const bool timed = mm_timing_on();
   if (use_tc) {
     // ---------------- tensor-core path: channels-last activations ----------------
     // layer i writes fp32 Y[p][cout] + GroupNorm partials; norm_split turns it into the packed FP16
@@ -232,31 +233,39 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       p.part = w.part;
       const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
       const float wps = wts->tc_scale[MMMOT_W_PN_WP1 + i];
+      const double cols = (double)P;
       if (i == 0) {
-        if (mm_debug_flags() & 2048) {                          // A/B: first layer as a thread-fed tcgen05 contraction
-          p.X = w.xt; p.x_ks = P;                               // fp32 [3][P] gather
-          MM_TRY(gemm_tc_launch<XM_DIRECT>(p, wp, wps, st, tc::OUT_CL));
-        } else {
-          pn_l1_stats_kernel<<<(int)tiles.size(), 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
-          MM_LAUNCH_CHECK();
-        }
+        if (timed) mm_timing_begin(st, MM_T_PN_L1, 2.0 * 64 * 3 * cols, 12.0 * cols);
+        pn_l1_stats_kernel<<<(int)tiles.size(), 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
+        MM_LAUNCH_CHECK();
+        if (timed) mm_timing_end(st);
       } else {                                                  // FP16 hi/lo planes [2][P][cin] via TMA
+        // compulsory traffic: operand planes in (4 B per element) + fp32 activation out (none for the statistics pass)
+        if (timed) mm_timing_begin(st, i == 4 ? MM_T_PN_L5A : MM_T_PN_L2 + (i - 1), 2.0 * cout[i] * cin[i] * cols,
+                                   4.0 * (cin[i] + (i == 4 ? 0 : cout[i])) * cols);
         MM_TRY(gemm_tma_launch_mat(p, wp, wps, i == 1 ? w.x1p : w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st));
+        if (timed) mm_timing_end(st);
       }
       MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
-      if (i == 0 && !(mm_debug_flags() & 2048)) {
-        pn_l1_apply_kernel<<<mm_cdiv(P * 16, 256), 256, 0, st>>>(points, q[0], q[1], w.sc, w.sh, w.seg, L, P, w.x1p);
+      if (i == 0) {
+        if (timed) mm_timing_begin(st, MM_T_PN_L1, 0.0, (12.0 + 4.0 * 64) * cols);
+        pn_l1_apply_kernel<<<mm_cdiv(P * 16, 256), 256, 0, st>>>(points, q[0], q[1], w.sc, w.sh, w.seg, L, P, w.x1p, ar.status());
         MM_LAUNCH_CHECK();
+        if (timed) mm_timing_end(st);
       } else if (i < 4) {
-        MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, i == 0 ? w.x1p : w.xp, st));
+        if (timed) mm_timing_begin(st, MM_T_PN_NORM, 0.0, 8.0 * cout[i] * cols);
+        MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, w.xp, st, ar.status()));
+        if (timed) mm_timing_end(st);
       } else {
         // second pass of the 1024-wide layer: recompute, GroupNorm + ReLU + per-detection mean in the epilogue
         // (its 1024 x P activation, 537 MB per frame-pair at cfg4, is never written)
         MM_CUDA(cudaMemsetAsync(w.segsum, 0, (size_t)ndet * 1024 * sizeof(unsigned long long), st));
         p.Y = nullptr; p.part = nullptr;
         p.sc = w.sc; p.sh = w.sh; p.seg = w.seg;
+        if (timed) mm_timing_begin(st, MM_T_PN_L5B, 2.0 * cout[i] * cin[i] * cols, 4.0 * cin[i] * cols);
         MM_TRY(gemm_tma_launch_mat(p, wp, wps, w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st, w.segsum));
+        if (timed) mm_timing_end(st);
         segsum_mean_kernel<<<mm_cdiv(1024L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 1024, ndet, w.gmean);
         MM_LAUNCH_CHECK();
       }
@@ -279,13 +288,17 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       p.addend = w.ut; p.seg = w.seg; p.ld_add = 512;
       const uint4* whp = (const uint4*)wts->w[MMMOT_W_PN_WHAP];
       const float whs = wts->tc_scale[MMMOT_W_PN_WHAP];
+      if (timed) mm_timing_begin(st, MM_T_PN_HEADA, 2.0 * 512 * 64 * (double)P, 4.0 * 64 * (double)P);
       MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st));
+      if (timed) mm_timing_end(st);
       MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1, w.sc, w.sh, st));
       // pass 2: recompute + GroupNorm + ReLU + per-detection mean
       MM_CUDA(cudaMemsetAsync(w.segsum, 0, (size_t)ndet * 512 * sizeof(unsigned long long), st));
       p.part = nullptr; p.sc = w.sc; p.sh = w.sh;
+      if (timed) mm_timing_begin(st, MM_T_PN_HEADB, 2.0 * 512 * 64 * (double)P, 4.0 * 64 * (double)P);
       MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, w.segsum));
+      if (timed) mm_timing_end(st);
       segsum_mean_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 512, ndet, w.hmean);
       MM_LAUNCH_CHECK();
     }

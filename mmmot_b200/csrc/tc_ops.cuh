@@ -4,7 +4,8 @@
 #pragma once
 #include "gemm_tma.cuh"
 
-__device__ __forceinline__ void split4_store(float4 x, __half* hi, __half* lo) {
+__device__ __forceinline__ void split4_store(float4 x, __half* hi, __half* lo, int* status) {
+  mm_range_flag(status, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
   __half h[4], l[4];
   tma::split_f16(x.x, h[0], l[0]); tma::split_f16(x.y, h[1], l[1]);
   tma::split_f16(x.z, h[2], l[2]); tma::split_f16(x.w, h[3], l[3]);
@@ -17,7 +18,7 @@ __device__ __forceinline__ void split4_store(float4 x, __half* hi, __half* lo) {
 // element and emitted as the FP16 hi/lo planes the next contraction's TMA loads read.
 static __global__ void norm_split_kernel(const float* __restrict__ in, long ldi, const float* __restrict__ sc,
                                          const float* __restrict__ sh, int C, long rows, int rows_per_group,
-                                         const int* __restrict__ seg, int L, __half* __restrict__ out) {
+                                         const int* __restrict__ seg, int L, __half* __restrict__ out, int* status) {
   const int c4n = C >> 2;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * c4n) return;
@@ -30,12 +31,13 @@ static __global__ void norm_split_kernel(const float* __restrict__ in, long ldi,
   float4 y;
   y.x = fmaxf(fmaf(x.x, a.x, b.x), 0.f); y.y = fmaxf(fmaf(x.y, a.y, b.y), 0.f);
   y.z = fmaxf(fmaf(x.z, a.z, b.z), 0.f); y.w = fmaxf(fmaf(x.w, a.w, b.w), 0.f);
-  split4_store(y, out + row * C + c, out + rows * C + row * C + c);
+  split4_store(y, out + row * C + c, out + rows * C + row * C + c, status);
 }
 
 static inline int norm_split(const float* in, long ldi, const float* sc, const float* sh, int C, long rows,
-                             int rows_per_group, const int* seg, int L, __half* out, cudaStream_t st) {
-  norm_split_kernel<<<mm_cdiv(rows * (C / 4), 256), 256, 0, st>>>(in, ldi, sc, sh, C, rows, rows_per_group, seg, L, out);
+                             int rows_per_group, const int* seg, int L, __half* out, cudaStream_t st, int* status) {
+  norm_split_kernel<<<mm_cdiv(rows * (C / 4), 256), 256, 0, st>>>(in, ldi, sc, sh, C, rows, rows_per_group, seg, L, out,
+                                                                 status);
   MM_LAUNCH_CHECK();
   return 0;
 }
@@ -63,30 +65,4 @@ static inline int transpose_f32(const float* src, float* dst, int rows, int cols
   transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols, groups);
   MM_LAUNCH_CHECK();
   return 0;
-}
-
-// Pairwise operand of the affinity contraction (reference modules/gcn.py:6-41) emitted directly as FP16 hi/lo
-// planes [2][G*N*M][512]:  x[(g*N + i)*M + j][c] = f[g][i][c] (*|-) f[g][N + j][c], from the channels-last
-// feature stacks fcl[g][L][512].  (fp32 x is never stored; 4 B/element like fp32 but already in the
-// tensor-core operand format.)
-template <int OP>
-static __global__ void pair_split_kernel(const float* __restrict__ fcl, int n, int m, long rows,
-                                         __half* __restrict__ out) {
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * 128) return;
-  const long row = idx >> 7;
-  const int c = (int)(idx & 127) * 4;
-  const int nm = n * m, L = n + m;
-  const int g = (int)(row / nm);
-  const int r = (int)(row - (long)g * nm);
-  const int i = r / m, j = r - i * m;
-  const float4 a = *reinterpret_cast<const float4*>(fcl + ((long)g * L + i) * 512 + c);
-  const float4 b = *reinterpret_cast<const float4*>(fcl + ((long)g * L + n + j) * 512 + c);
-  float4 x;
-  if (OP == MMMOT_AFF_MULTIPLY) { x.x = a.x * b.x; x.y = a.y * b.y; x.z = a.z * b.z; x.w = a.w * b.w; }
-  else if (OP == MMMOT_AFF_MINUS_ABS) {
-    x.x = fabsf((a.x - b.x) * 0.5f); x.y = fabsf((a.y - b.y) * 0.5f);
-    x.z = fabsf((a.z - b.z) * 0.5f); x.w = fabsf((a.w - b.w) * 0.5f);
-  } else { x.x = (a.x - b.x) * 0.5f; x.y = (a.y - b.y) * 0.5f; x.z = (a.z - b.z) * 0.5f; x.w = (a.w - b.w) * 0.5f; }
-  split4_store(x, out + row * 512 + c, out + rows * 512 + row * 512 + c);
 }

@@ -70,15 +70,16 @@ def crop_points(points, boxes_lidar, without_reflectivity=True):
     boxes = np.asarray(boxes_lidar, dtype=np.float32).reshape(-1, 7)
     n = boxes.shape[0]
     dev = points.device
-    planes = torch.from_numpy(np.ascontiguousarray(box_planes(boxes))).to(dev)
-    ws = torch.empty(int(lib.mmmot_crop_workspace(P, n)), dtype=torch.uint8, device=dev)
-    split = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib.mmmot_crop_count(vp(points), P, C, vp(planes), n, vp(split), vp(ws), ws.numel(), st), "mmmot_crop_count")
-    split_h = split.cpu()                      # output size is data dependent: one sync, like the reference's host loop
-    out_c = 3 if without_reflectivity else min(C, 4)
-    out = torch.empty(int(split_h[-1]), out_c, device=dev)
-    _lib.check(lib.mmmot_crop_scatter(vp(points), P, C, vp(planes), n, vp(split), out_c, vp(out), vp(ws), ws.numel(), st),
-               "mmmot_crop_scatter")
+    with torch.cuda.device(dev):            # the library works on the CURRENT device
+        planes = torch.from_numpy(np.ascontiguousarray(box_planes(boxes))).to(dev)
+        ws = torch.empty(int(lib.mmmot_crop_workspace(P, n)), dtype=torch.uint8, device=dev)
+        split = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.mmmot_crop_count(vp(points), P, C, vp(planes), n, vp(split), vp(ws), ws.numel(), st), "mmmot_crop_count")
+        split_h = split.cpu()                      # output size is data dependent: one sync, like the reference's host loop
+        out_c = 3 if without_reflectivity else min(C, 4)
+        out = torch.empty(int(split_h[-1]), out_c, device=dev)
+        _lib.check(lib.mmmot_crop_scatter(vp(points), P, C, vp(planes), n, vp(split), out_c, vp(out), vp(ws), ws.numel(), st),
+                   "mmmot_crop_scatter")
     return out, split_h.long()

@@ -40,10 +40,11 @@ def solve_batch(det, link, new, end, n, m):
     match = torch.empty(B, n, dtype=torch.int32, device=dev)
     ws = torch.empty(int(lib.mmmot_lp_workspace(B, n, m)), dtype=torch.uint8, device=dev)
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib.mmmot_lp_assign(vp(det), sd, vp(link), sl, vp(new), sn, vp(end), se, B, n, m,
-                                   vp(a_det), vp(a_link), vp(a_new), vp(a_end), vp(match),
-                                   vp(ws), ws.numel(), st), "mmmot_lp_assign")
+    with torch.cuda.device(dev):            # the library works on the CURRENT device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.mmmot_lp_assign(vp(det), sd, vp(link), sl, vp(new), sn, vp(end), se, B, n, m,
+                                       vp(a_det), vp(a_link), vp(a_new), vp(a_end), vp(match),
+                                       vp(ws), ws.numel(), st), "mmmot_lp_assign")
     return {"assign_det": a_det, "assign_link": a_link, "assign_new": a_new, "assign_end": a_end,
             "match": match}
 

@@ -137,6 +137,7 @@ class TrackingNet(nn.Module):
                    lib.mmmot_affinity_workspace(pairs, n, m))
         ws = self._workspace(need, dev)
         wsp, wsn = ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel())
+        _lib.check(lib.mmmot_status_reset(wsp, st), "mmmot_status_reset")
         feats = out["feats"][p0:p0 + pairs]
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         _lib.check(lib.mmmot_appearance_fwd(wts.ptr, vp(crops), pairs * L, H, W, L, vp(feats), wsp, wsn, st),
@@ -144,13 +145,26 @@ class TrackingNet(nn.Module):
         hs = split_host.numpy()
         _lib.check(lib.mmmot_pointnet_fwd(wts.ptr, vp(points), vp(split_dev), ctypes.c_void_p(hs.ctypes.data),
                                           pairs, L, vp(feats), wsp, wsn, st), "mmmot_pointnet_fwd")
-        _lib.check(lib.mmmot_fusion_det_fwd(wts.ptr, _lib.FUSION[self.score_fusion_arch],
+        _lib.check(lib.mmmot_fusion_det_fwd(wts.ptr, _lib.FUSION[self.score_fusion_arch], self._score_flags(),
                                             float(self.neg_threshold), pairs, L, vp(feats),
                                             vp(out["det"][p0:p0 + pairs]), wsp, wsn, st), "mmmot_fusion_det_fwd")
         _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op],
                                           _lib.SOFTMAX.get(self.softmax_mode, 0), pairs, n, m, vp(feats),
                                           vp(out["link"][p0:p0 + pairs]), vp(out["new"][p0:p0 + pairs]),
                                           vp(out["end"][p0:p0 + pairs]), wsp, wsn, st), "mmmot_affinity_fwd")
+        # the status word (FP16 range flag) of this chunk, accumulated into out["status"] in stream order
+        out["status"] |= ws[:4].view(torch.int32)
+
+    def _score_flags(self):
+        """reference tracking_net.py:153-162: sigmoid only when 'cls' is in score_arch; the neg_threshold step is
+        the eval branch."""
+        return (_lib.SCORE_SIGMOID if "cls" in self.score_arch else 0) | _lib.SCORE_THRESHOLD
+
+    @staticmethod
+    def _raise_on_status(status):
+        """`status`: the int32 word forward_batch returns (device tensor or int)."""
+        if int(status) & 1:
+            _lib.check(-4, "mmmot_b200.TrackingNet forward")
 
     def _pick_chunk(self, B, n, m, P_per_pair, H, W, dev):
         if self.chunk_pairs:
@@ -169,7 +183,7 @@ class TrackingNet(nn.Module):
         return c
 
     @torch.no_grad()
-    def forward_batch(self, crops, points, points_split, n, m=None, keep_feats=False):
+    def forward_batch(self, crops, points, points_split, n, m=None, keep_feats=False, check=True):
         """B independent frame-pairs, each with n previous and m next detections.
 
         crops         (B*(n+m)) x 3 x H x W  fp32, CUDA
@@ -177,7 +191,10 @@ class TrackingNet(nn.Module):
         points_split  (B*(n+m) + 1,) int     CSR offsets, CPU tensor (the reference reads it with
                                              .item() per detection: modules/point_net.py:33-35)
         returns dict: det B x 3 x L, link B x 3 x n x m, new B x 3 x m, end B x 3 x n (un-padded),
-                      trans [1x3x3, 1x64x64]; per-pair semantics identical to ``forward``.
+                      trans [1x3x3, 1x64x64]; per-pair semantics identical to ``forward``; "status": the library's
+                      status word (int32 device tensor; bit 0 = an activation left FP16's range, MMMOT_E_RANGE).
+        check=True (default) reads the status word back (one host sync) and raises MmmotError when it is set;
+        pipelined callers pass check=False and test ``out["status"]`` together with the results they copy back.
         """
         if self.training:
             raise NotImplementedError("mmmot_b200.TrackingNet implements the eval-mode forward only (SURVEY §8f N4)")
@@ -196,24 +213,28 @@ class TrackingNet(nn.Module):
         B = crops.shape[0] // L
         H, W = crops.shape[-2:]
         out = {
+            "status": torch.zeros(1, dtype=torch.int32, device=dev),
             "feats": torch.empty(B, 3, 512, L, device=dev),
             "det": torch.empty(B, 3, L, device=dev),
             "link": torch.empty(B, 3, n, m, device=dev),
             "new": torch.empty(B, 3, m, device=dev),
             "end": torch.empty(B, 3, n, device=dev),
         }
-        chunk = self._pick_chunk(B, n, m, int(split[-1]) / B, H, W, dev)
-        for p0 in range(0, B, chunk):
-            pc = min(chunk, B - p0)
-            s_host = split[p0 * L:(p0 + pc) * L + 1]
-            off = int(s_host[0])
-            s_host = (s_host - off).contiguous()
-            s_dev = s_host.to(dev, non_blocking=False)
-            self._run_chunk(lib, wts, crops[p0 * L:(p0 + pc) * L], points[off:off + int(s_host[-1])],
-                            s_dev, s_host, pc, n, m, out, p0)
+        with torch.cuda.device(dev):        # the library works on the CURRENT device
+            chunk = self._pick_chunk(B, n, m, int(split[-1]) / B, H, W, dev)
+            for p0 in range(0, B, chunk):
+                pc = min(chunk, B - p0)
+                s_host = split[p0 * L:(p0 + pc) * L + 1]
+                off = int(s_host[0])
+                s_host = (s_host - off).contiguous()
+                s_dev = s_host.to(dev, non_blocking=False)
+                self._run_chunk(lib, wts, crops[p0 * L:(p0 + pc) * L], points[off:off + int(s_host[-1])],
+                                s_dev, s_host, pc, n, m, out, p0)
         out["trans"] = [wts.trans1.unsqueeze(0).clone(), wts.trans2.unsqueeze(0).clone()]
         if not keep_feats:
             del out["feats"]
+        if check:
+            self._raise_on_status(out["status"])
         return out
 
     @torch.no_grad()
@@ -230,22 +251,25 @@ class TrackingNet(nn.Module):
         link = torch.empty(B, 3, n, m, device=dev)
         new = torch.empty(B, 3, m, device=dev)
         end = torch.empty(B, 3, n, device=dev)
-        ws = self._workspace(lib.mmmot_affinity_workspace(B, n, m), dev)
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op],
-                                          _lib.SOFTMAX.get(self.softmax_mode, 0), B, n, m, vp(feats),
-                                          vp(link), vp(new), vp(end), vp(ws), ws.numel(), st),
-                   "mmmot_affinity_fwd")
+        with torch.cuda.device(dev):
+            ws = self._workspace(lib.mmmot_affinity_workspace(B, n, m), dev)
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.mmmot_status_reset(vp(ws), st), "mmmot_status_reset")
+            _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op],
+                                              _lib.SOFTMAX.get(self.softmax_mode, 0), B, n, m, vp(feats),
+                                              vp(link), vp(new), vp(end), vp(ws), ws.numel(), st),
+                       "mmmot_affinity_fwd")
+            _lib.check(lib.mmmot_status_check(vp(ws), st), "mmmot_affinity_fwd")
         return link, new, end
 
     @torch.no_grad()
-    def predict_batch(self, crops, points, points_split, n, m=None):
+    def predict_batch(self, crops, points, points_split, n, m=None, check=True):
         """forward_batch + association programme on the ``test_mode`` stack, all on the device.
         Returns forward_batch's dict plus assign_{det,link,new,end} and match (B x n int32)."""
         from .solvers import solve_batch
         m = n if m is None else m
-        out = self.forward_batch(crops, points, points_split, n, m)
+        out = self.forward_batch(crops, points, points_split, n, m, check=check)
         B, t = out["det"].shape[0], self.test_mode
         zn = out["det"].new_zeros(B, 3, n)
         zm = out["det"].new_zeros(B, 3, m)

@@ -19,7 +19,9 @@ import torch
 
 def _build(det_score, link_score, new_score, end_score, det_split):
     """Variable layout [y_det(L) | y_new(L) | y_end(L) | y_link_0(N0*M0) | ...], objective
-    vector c (maximise c.y) and equality rows A y = 0 exactly as solvers.py:83-111 adds them."""
+    vector c (maximise c.y) and equality rows A y = 0 exactly as solvers.py:83-111 adds them
+    (A is returned as a scipy.sparse CSR matrix: 3 + M non-zeros per row)."""
+    from scipy.sparse import csr_matrix
     split = [int(s) for s in det_split]
     L = int(det_score.shape[0])
     assert sum(split) == L
@@ -32,37 +34,37 @@ def _build(det_score, link_score, new_score, end_score, det_split):
         off_link.append(off_link[-1] + l.size)
     nvar = off_link[-1]
     c = np.concatenate([det, new, end] + [l.reshape(-1) for l in links])
-    rows = []
+    ri, ci, vals = [], [], []
+    nrow = 0
+
+    def add_row(cols, coef):
+        nonlocal nrow
+        ri.append(np.full(len(cols), nrow))
+        ci.append(np.asarray(cols))
+        vals.append(np.asarray(coef, dtype=np.float64))
+        nrow += 1
     start = 0
     for i in range(len(split) - 1):
         n, m = split[i], split[i + 1]
         assert links[i].shape == (n, m)
         for j in range(n):                      # end + successors = det          (:88-98)
-            r = np.zeros(nvar)
             idx = start + j
-            r[2 * L + idx] = 1
-            r[idx] = -1
-            r[off_link[i] + j * m: off_link[i] + (j + 1) * m] = 1
-            rows.append(r)
+            succ = np.arange(off_link[i] + j * m, off_link[i] + (j + 1) * m)
+            add_row(np.concatenate([[2 * L + idx, idx], succ]), np.concatenate([[1.0, -1.0], np.ones(m)]))
             if i == 0:                          # first frame: new = det           (:99-101)
-                r = np.zeros(nvar)
-                r[L + idx] = 1
-                r[idx] = -1
-                rows.append(r)
+                add_row([L + idx, idx], [1.0, -1.0])
         start += n
         for k in range(m):                      # new + predecessors = det        (:103-109)
-            r = np.zeros(nvar)
             idx = start + k
-            r[L + idx] = 1
-            r[idx] = -1
-            r[off_link[i] + k: off_link[i] + n * m: m] = 1
-            rows.append(r)
+            pred = np.arange(off_link[i] + k, off_link[i] + n * m, m)
+            add_row(np.concatenate([[L + idx, idx], pred]), np.concatenate([[1.0, -1.0], np.ones(n)]))
             if i == len(split) - 2:             # last frame: end = det           (:110-111)
-                r = np.zeros(nvar)
-                r[2 * L + idx] = 1
-                r[idx] = -1
-                rows.append(r)
-    return c, np.asarray(rows), L, split, off_link
+                add_row([2 * L + idx, idx], [1.0, -1.0])
+    if nrow:
+        A = csr_matrix((np.concatenate(vals), (np.concatenate(ri), np.concatenate(ci))), shape=(nrow, nvar))
+    else:
+        A = csr_matrix((0, nvar))
+    return c, A, L, split, off_link
 
 
 def _unpack(y, L, split, off_link, like):
@@ -80,7 +82,7 @@ def milp_solve(det_score, link_score, new_score, end_score, det_split, exclude=N
     measure the optimality gap to the second-best solution)."""
     from scipy.optimize import Bounds, LinearConstraint, milp
     c, A, L, split, off = _build(det_score, link_score, new_score, end_score, det_split)
-    cons = [LinearConstraint(A, 0, 0)] if len(A) else []
+    cons = [LinearConstraint(A, 0, 0)] if A.shape[0] else []
     if exclude is not None:
         e = np.asarray(exclude, dtype=np.float64)
         cons.append(LinearConstraint((2 * e - 1)[None, :], -np.inf, e.sum() - 1))
@@ -120,7 +122,7 @@ def brute_force(det_score, link_score, new_score, end_score, det_split):
                     y[n + k] = 1
                     y[L + n + k] = 1
                     y[2 * L + n + k] = 1
-            assert not len(A) or np.all(A @ y == 0)
+            assert not A.shape[0] or np.all(A @ y == 0)
             v = float(c @ y)
             if v > best:
                 second, best, best_y = best, v, y
@@ -137,3 +139,41 @@ def objective(det_score, link_score, new_score, end_score, assign):
     for l, a in zip(link_score, a_link):
         v = v + (l.double() * a.double()).sum()
     return float(v)
+
+
+def assignment_solve(det_score, link_score, new_score, end_score, det_split):
+    """Second, independent oracle for 2-frame samples: the (N+M) x (M+N) assignment reduction of the
+    programme (derivation from solvers.py:83-111) solved by ``scipy.optimize.
+    linear_sum_assignment`` — rows = previous detections + one private "next det stays unmatched"
+    row per next detection, columns = next detections + one private "track ends / inactive" column
+    per previous detection.  Returns the same tuple as ``milp_solve`` (assignment, objective)."""
+    from scipy.optimize import linear_sum_assignment
+    n, m = (int(s) for s in det_split)
+    d = np.asarray(det_score, dtype=np.float64).reshape(-1)
+    nw = np.asarray(new_score, dtype=np.float64).reshape(-1)
+    e = np.asarray(end_score, dtype=np.float64).reshape(-1)
+    l = np.asarray(link_score[0], dtype=np.float64).reshape(n, m)
+    u = d[:n] + nw[:n] + e[:n]                 # prev det active, track ends here
+    v = d[n:] + e[n:] + nw[n:]                 # next det active, track starts here
+    NEG = -1e9
+    C = np.full((n + m, m + n), NEG)
+    C[:n, :m] = (d[:n] + nw[:n])[:, None] + (d[n:] + e[n:])[None, :] + l
+    C[np.arange(n), m + np.arange(n)] = np.maximum(u, 0.0)
+    C[n + np.arange(m), np.arange(m)] = np.maximum(v, 0.0)
+    C[n:, m:] = 0.0
+    rr, cc = linear_sum_assignment(C, maximize=True)
+    L = n + m
+    a_det, a_new, a_end = np.zeros(L), np.zeros(L), np.zeros(L)
+    a_link = np.zeros((n, m))
+    for r, c in zip(rr, cc):
+        if r < n and c < m:
+            a_link[r, c] = 1
+            a_det[r] = a_new[r] = 1
+            a_det[n + c] = a_end[n + c] = 1
+        elif r < n and c == m + r and u[r] > 0:
+            a_det[r] = a_new[r] = a_end[r] = 1
+        elif r >= n and c == r - n and v[c] > 0:
+            a_det[n + c] = a_new[n + c] = a_end[n + c] = 1
+    t = lambda a: torch.as_tensor(a, dtype=det_score.dtype)
+    assign = (t(a_det), [t(a_link[None])], t(a_new), t(a_end))
+    return assign, float(C[rr, cc].sum())

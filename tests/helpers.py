@@ -20,6 +20,34 @@ def relerr(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+# Element-wise companion of the max-norm metric: |a-b| <= RTOL_EL*|ref| + ATOL_EL.
+# The absolute term covers entries that are themselves at fp32 round-off of the tensor's scale
+# (softmax tails, ReLU zeros): 1e-6 is ~1e-2 of the max-norm bound for tensors of scale 1e-2..1.
+RTOL_EL, ATOL_EL = 1e-4, 1e-6
+# No element may miss that bound by more than this factor (the few that exceed it at all are counted and reported).
+WORST_EL = 4.0
+
+
+def frac_outside(a, b, rtol=RTOL_EL, atol=ATOL_EL):
+    """Fraction of elements violating |a-b| <= rtol*|ref| + atol, and the worst ratio |a-b| / (rtol*|ref| + atol)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    bound = rtol * b.abs() + atol
+    ratio = (a - b).abs() / bound
+    return float((ratio > 1).double().mean()), float(ratio.max())
+
+
+def check_close(a, ref, tol, what, report=None, max_outside=0.0):
+    """Both metrics: max-norm relative error < tol and at most `max_outside` of the elements outside the
+    element-wise bound.  Appends (what, max-norm error, fraction outside, worst element ratio) to `report`."""
+    e = relerr(a, ref)
+    fo, worst = frac_outside(a, ref)
+    if report is not None:
+        report.append((what, e, fo, worst))
+    assert e < tol, f"{what}: max-norm relative error {e:.3e} >= {tol:g}"
+    assert fo <= max_outside, f"{what}: {fo:.3e} of the elements outside |a-b| <= {RTOL_EL:g}|ref| + {ATOL_EL:g} (worst x{worst:.2f})"
+    assert worst < WORST_EL, f"{what}: an element misses the element-wise bound by x{worst:.2f}"
+
+
 def golden_cases():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))):

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for n in names:
         assert getattr(lib, n) is not None
     lib.mmmot_abi_version.restype = ctypes.c_int
-    assert lib.mmmot_abi_version() == 1
+    assert lib.mmmot_abi_version() == _lib.ABI_VERSION == int(re.search(r"MMMOT_ABI_VERSION (\d+)", open(_lib.HEADER_PATH).read()).group(1))
 
 
 def test_python_enums_match_header():

@@ -4,13 +4,17 @@ max|a-b| / max|ref|; assignment outputs bit-exact."""
 import pytest
 import torch
 
-from helpers import TOL, case_tol, det_close, golden_cases, relerr
+from helpers import TOL, case_tol, check_close, det_close, frac_outside, golden_cases, relerr
 import mmmot_b200
 from mmmot_b200.synthetic import synthetic_batch, synthetic_pair, synthetic_state_dict
 from oracle import lp_ref, torch_ref
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases()
+# fraction of elements allowed outside the element-wise bound |a-b| <= 1e-4|ref| + 1e-6 (helpers.frac_outside; reported by
+# every test that uses it).  Measured on the cfg4 pair: 2e-5 of the dual_add link entries, the worst by a factor 1.003 —
+# softmax outputs of ~5e-3 whose absolute error (1.5e-6) is what the 4e-5 max-norm error leaves at that magnitude.
+ELEM_OUTSIDE = 1e-3
 
 
 def make_net(fusion, op, sm, thr, seed):
@@ -29,10 +33,18 @@ def engine(request):
     mmmot_b200.set_engine("auto")
 
 
-@pytest.mark.parametrize("M,K,S", [(128, 32, 256), (256, 96, 512), (64, 70, 300), (512, 512, 4099), (1024, 128, 1000),
+def _planes(x):
+    """fp32 -> FP16 (hi, lo) planes stacked on a new leading axis (the tcgen05 engines' operand format)."""
+    hi = x.half()
+    return torch.stack([hi, (x - hi.float()).half()]).contiguous()
+
+
+@pytest.mark.parametrize("M,K,S", [(128, 32, 256), (256, 96, 512), (64, 64, 300), (512, 512, 4099), (1024, 128, 1000),
                                    (128, 4608, 2048)])
-def test_tcgen05_contraction_vs_fp64(M, K, S):
-    """The split-BF16 tensor-core contraction alone (C ABI test hook) against an fp64 matmul."""
+def test_contraction_engines_vs_fp64(M, K, S):
+    """Each contraction engine alone (C ABI test hooks) against an fp64 matmul: the FP32 FFMA engine, the TMA-fed
+    tcgen05 engine (FP16 hi/lo planes in, fp32 out) and the generated-operand tcgen05 engine (GroupNorm+ReLU producer,
+    fp32 channels-last in / out)."""
     import ctypes
     from mmmot_b200 import _lib
     from mmmot_b200.weights import pack_tc
@@ -44,10 +56,59 @@ def test_tcgen05_contraction_vs_fp64(M, K, S):
     Wt_d, X_d, b_d = Wt.cuda(), X.cuda(), b.cuda()
     Wp, wps = pack_tc(Wt)
     Wp = Wp.cuda()
-    for eng in (1, 2):
-        Y = torch.full((M, S), float("nan"), device="cuda")
-        assert lib.mmmot_debug_linear(vp(Wt_d), vp(Wp), wps, vp(b_d), vp(X_d), vp(Y), M, K, S, eng, None) == 0
-        assert relerr(Y, ref) < 3e-5, eng
+    Y = torch.full((M, S), float("nan"), device="cuda")
+    assert lib.mmmot_debug_linear(vp(Wt_d), None, 0.0, vp(b_d), vp(X_d), vp(Y), M, K, S, 1, None) == 0
+    assert relerr(Y, ref) < 3e-5, "fp32 engine"
+    # TMA-fed engine: X as channels-last planes [2][S][K], Y [S][M]
+    Xp = _planes(X.t().contiguous()).cuda()
+    Y2 = torch.full((S, M), float("nan"), device="cuda")
+    assert lib.mmmot_debug_linear_planar(vp(Wp), wps, vp(b_d), vp(Xp), vp(Y2), M, K, S, None) == 0
+    assert relerr(Y2.t(), ref) < 3e-5, "tma engine"
+    # generated-operand engine: Y[S][M] = relu(X[S][K]*sc + sh) W^T + b, fp32 channels-last in and out
+    if K <= 512 and K % 32 == 0:
+        sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.3
+        ref3 = Wt.double().t() @ torch.relu(X.double() * sc.double()[:, None] + sh.double()[:, None]) + b.double()[:, None]
+        Xc = X.t().contiguous().cuda()
+        Y3 = torch.full((S, M), float("nan"), device="cuda")
+        assert lib.mmmot_debug_linear_gen(vp(Wp), wps, vp(b_d), vp(Xc), vp(sc.cuda()), vp(sh.cuda()), vp(Y3), M, K, S, None) == 0
+        torch.cuda.synchronize()
+        assert relerr(Y3.t(), ref3) < 3e-5, "gen engine"
+
+
+def test_fp16_range_is_reported_not_clamped():
+    """activations >= 65504 saturate in the FP16 hi/lo conversion of the tensor-core path; the
+    library raises MMMOT_E_RANGE instead of returning clamped results.  The FP32 engine has no such limit."""
+    from mmmot_b200 import _lib
+    net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 3)
+    dets, info, split = synthetic_pair(16, 16, 32, 32, seed=8)
+    args = (info["points"][0].cuda(), info["points_split"][0], 16, 16)
+    mmmot_b200.set_engine("tcgen05")
+    try:
+        o = net.forward_batch(dets.cuda(), *args)
+        assert int(o["status"]) == 0
+        with pytest.raises(_lib.MmmotError, match="MMMOT_E_RANGE"):
+            net.forward_batch(dets.cuda() * 1e6, *args)
+        o = net.forward_batch(dets.cuda() * 1e6, *args, check=False)     # deferred check: the flag travels with the outputs
+        assert int(o["status"]) & 1
+        mmmot_b200.set_engine("fp32")
+        o = net.forward_batch(dets.cuda() * 1e6, *args)
+        assert int(o["status"]) == 0 and torch.isfinite(o["link"]).all()
+    finally:
+        mmmot_b200.set_engine("auto")
+
+
+def test_score_arch_branch_reg_has_no_sigmoid():
+    """reference tracking_net.py:153-156: the sigmoid is applied only when 'cls' is in score_arch."""
+    dets, info, split = synthetic_pair(6, 6, 24, 32, seed=2)
+    outs = {}
+    for arch in ("branch_cls", "branch_reg"):
+        net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch=arch, score_fusion_arch="A", neg_threshold=-10.0,
+                                     test_mode=2, dropblock=0)
+        net.load_state_dict(synthetic_state_dict("A", seed=6))
+        net.cuda().eval()
+        outs[arch] = net(dets.cuda(), {k: v.cuda() for k, v in info.items()}, split)[0]
+    assert torch.allclose(torch.sigmoid(outs["branch_reg"]), outs["branch_cls"], atol=1e-6)
+    assert (outs["branch_reg"].abs() > 1e-3).any()
 
 
 @pytest.mark.parametrize("g", CASES, ids=[c["case"][0] for c in CASES])
@@ -137,20 +198,32 @@ def _rand_lp(g, n, m, B=1):
     return det, link, new, end
 
 
-@pytest.mark.parametrize("n,m", [(1, 1), (3, 2), (8, 8), (7, 19), (32, 32), (64, 64)])
+def _assert_same_assignment(got, ref):
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1][0], ref[1][0])
+    assert torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (3, 2), (8, 8), (7, 19), (16, 16), (32, 32), (64, 64), (128, 128), (100, 128),
+                                 (256, 256)])
 def test_lp_bit_exact_vs_milp_oracle(n, m):
+    """Every N of BASELINE's sweep (8..256, plus ragged shapes): the warp-per-pair Hungarian kernel returns the
+    SAME 0/1 tensors as the MILP restatement of solvers.py:17-111 (HiGHS) and as the independent assignment
+    reduction solved by scipy.linear_sum_assignment.  Random continuous scores: the optimum is unique."""
     g = torch.Generator().manual_seed(100 + n + m)
-    B = 6
+    B = 6 if n <= 64 else 4
     det, link, new, end = _rand_lp(g, n, m, B)
     r = mmmot_b200.solve_batch(det.cuda(), link.cuda(), new.cuda(), end.cuda(), n, m)
     for b in range(B):
         (a, obj, y) = lp_ref.milp_solve(det[b], [link[b:b + 1]], new[b], end[b], [n, m])
+        a2, obj2 = lp_ref.assignment_solve(det[b], [link[b:b + 1]], new[b], end[b], [n, m])
         got = (r["assign_det"][b].cpu(), [r["assign_link"][b:b + 1].cpu()], r["assign_new"][b].cpu(), r["assign_end"][b].cpu())
         assert abs(lp_ref.objective(det[b], [link[b:b + 1]], new[b], end[b], got) - obj) < 1e-9
-        assert torch.equal(got[0], a[0]) and torch.equal(got[1][0], a[1][0])
-        assert torch.equal(got[2], a[2]) and torch.equal(got[3], a[3])
+        assert abs(obj - obj2) < 1e-8
+        _assert_same_assignment(got, a)
+        _assert_same_assignment(got, a2)
         mt = r["match"][b].cpu()
         assert torch.equal(mt >= 0, a[1][0][0].sum(1) > 0)
+        assert torch.equal(mt.clamp_min(0)[mt >= 0].long(), a[1][0][0].argmax(1)[mt >= 0])
 
 
 def test_lp_reference_signature_on_forward_outputs():
@@ -217,11 +290,58 @@ def test_cfg4_full_size_pair_matches_oracle():
     torch.set_num_threads(min(16, torch.get_num_threads()))
     ref_det, ref_link, ref_new, ref_end, _ = torch_ref.forward(sd, dets, info, split, "C", "minus_abs", "dual_add", 0.2)
     det, link, new, end, _ = net(dets.cuda(), {k: v.cuda() for k, v in info.items()}, split)
-    assert relerr(link[0], ref_link[0]) < TOL
-    assert relerr(new, ref_new) < TOL and relerr(end, ref_end) < TOL
+    rep = []
+    check_close(link[0], ref_link[0], TOL, "link", rep, max_outside=ELEM_OUTSIDE)
+    check_close(new, ref_new, TOL, "new", rep, max_outside=ELEM_OUTSIDE)
+    check_close(end, ref_end, TOL, "end", rep, max_outside=ELEM_OUTSIDE)
     assert det_close(det, ref_det, 0.2, TOL)
-    # and the assignment computed from both score sets agrees wherever the LP optimum is unambiguous
-    a = mmmot_b200.ortools_solve(det[2], [link[0][2:3]], new[2], end[2], split)
-    b = mmmot_b200.ortools_solve(ref_det[2].cuda(), [ref_link[0][2:3].cuda()], ref_new[2].cuda(), ref_end[2].cuda(), split)
-    agree = (a[1][0] == b[1][0]).float().mean().item()
-    assert agree > 0.999, agree
+    print("cfg4 pair (what, max-norm rel err, fraction outside element-wise bound, worst ratio):", rep)
+    # (1) identical inputs -> identical indices: the GPU solver on the ORACLE's score tensors equals the MILP
+    #     restatement and the assignment reduction bit for bit (north_star: "assignment indices bit-exact")
+    t = 2
+    b = mmmot_b200.ortools_solve(ref_det[t].cuda(), [ref_link[0][t:t + 1].cuda()], ref_new[t].cuda(), ref_end[t].cuda(), split)
+    b = (b[0].cpu(), [b[1][0].cpu()], b[2].cpu(), b[3].cpu())
+    (mil, obj, y) = lp_ref.milp_solve(ref_det[t], [ref_link[0][t:t + 1]], ref_new[t], ref_end[t], [n, n])
+    lsa, _ = lp_ref.assignment_solve(ref_det[t], [ref_link[0][t:t + 1]], ref_new[t], ref_end[t], [n, n])
+    _assert_same_assignment(b, mil)
+    _assert_same_assignment(b, lsa)
+    # (2) end to end (GPU scores -> GPU solver) against (oracle scores -> oracle solver): the two score sets differ by
+    #     fp32 round-off, so the optimum can only move if the gap to the second-best solution is smaller than the
+    #     total score perturbation.  Measure both; demand exact equality whenever the gap exceeds the perturbation.
+    a = mmmot_b200.ortools_solve(det[t], [link[0][t:t + 1]], new[t], end[t], split)
+    a = (a[0].cpu(), [a[1][0].cpu()], a[2].cpu(), a[3].cpu())
+    perturb = float((det[t].cpu() - ref_det[t]).abs().sum() + (link[0][t].cpu() - ref_link[0][t]).abs().sum()
+                    + (new[t].cpu() - ref_new[t]).abs().sum() + (end[t].cpu() - ref_end[t]).abs().sum())
+    (_, obj2, _) = lp_ref.milp_solve(ref_det[t], [ref_link[0][t:t + 1]], ref_new[t], ref_end[t], [n, n], exclude=y)
+    gap = obj - obj2
+    same = all(torch.equal(p, q) for p, q in ((a[0], mil[0]), (a[1][0], mil[1][0]), (a[2], mil[2]), (a[3], mil[3])))
+    print(f"cfg4 pair: LP optimum {obj:.6f}, second-best gap {gap:.3e}, L1 score perturbation {perturb:.3e}, identical={same}")
+    if gap > perturb:
+        assert same, (gap, perturb)
+    else:   # near-tie: the GPU-side optimum must still be optimal to within the perturbation under the oracle's scores
+        got = lp_ref.objective(ref_det[t], [ref_link[0][t:t + 1]], ref_new[t], ref_end[t], a)
+        assert obj - got <= perturb + 1e-9, (obj, got, perturb)
+
+
+# ------------------------------------------------------------------ BASELINE configs at their stated shapes
+@pytest.mark.parametrize("name,fusion,op,sm,n,pts,hw", [
+    ("cfg2", "A", "multiply", "none", 32, 128, 64),       # BASELINE configs[1]: pp_pv_40e_mul_A, N=32, 64x64 crops
+    ("cfg3", "C", "multiply", "none", 64, 512, 64),       # BASELINE configs[2]: pp_pv_40e_mul_C, N=64, P=512
+    ("crop224", "C", "minus_abs", "dual_add", 4, 96, 224),  # the reference's real crop size (test_seq_dataset.py:217-218)
+])
+def test_full_forward_at_baseline_config(name, fusion, op, sm, n, pts, hw):
+    """Full forward (all five outputs + the feature stacks) of one frame-pair at the shapes BASELINE.json states for
+    cfg2 / cfg3, and a multi-detection pair at 224x224 crops, against the oracle; max-norm and element-wise metrics."""
+    net, sd = make_net(fusion, op, sm, 0.2, 21)
+    dets, info, split = synthetic_pair(n, n, pts, hw, seed=300 + n, ragged=(name == "crop224"))
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    (rdet, rlink, rnew, rend, _), st = torch_ref.forward(sd, dets, info, split, fusion, op, sm, 0.2, return_stages=True)
+    o = net.forward_batch(dets.cuda(), info["points"][0].cuda(), info["points_split"][0], n, n, keep_feats=True)
+    rep = []
+    for s_ in range(3):
+        check_close(o["feats"][0, s_], st["feats"][s_], TOL, f"{name} feats[{s_}]", rep, max_outside=ELEM_OUTSIDE)
+    check_close(o["link"][0], rlink[0], TOL, f"{name} link", rep, max_outside=ELEM_OUTSIDE)
+    check_close(o["new"][0], rnew[:, n:], TOL, f"{name} new", rep, max_outside=ELEM_OUTSIDE)
+    check_close(o["end"][0], rend[:, :n], TOL, f"{name} end", rep, max_outside=ELEM_OUTSIDE)
+    assert det_close(o["det"][0], rdet, 0.2, TOL)
+    print(name, rep)

@@ -18,8 +18,16 @@ for K in (512, 1152, 2304, 4608):
         Wp, wps = pack_tc(Wt)
         res = {}
         for eng in (1, 2):
-            Y = torch.zeros(M, S, device="cuda")
-            lib.mmmot_debug_linear(vp(Wt.cuda()), vp(Wp.cuda()), wps, None, vp(X.cuda()), vp(Y), M, K, S, eng, None)
+            if eng == 1:
+                Y = torch.zeros(M, S, device="cuda")
+                lib.mmmot_debug_linear(vp(Wt.cuda()), None, 0.0, None, vp(X.cuda()), vp(Y), M, K, S, 1, None)
+            else:       # TMA-fed tcgen05 engine: channels-last FP16 hi/lo planes in, Y[S][M] out
+                Xc = X.t().contiguous()
+                hi = Xc.half()
+                Xp = torch.stack([hi, (Xc - hi.float()).half()]).contiguous().cuda()
+                Yt = torch.zeros(S, M, device="cuda")
+                lib.mmmot_debug_linear_planar(vp(Wp.cuda()), wps, None, vp(Xp), vp(Yt), M, K, S, None)
+                Y = Yt.t()
             torch.cuda.synchronize()
             e = (Y.double().cpu() - ref)
             rel = e / ref.abs().clamp_min(1e-30)
