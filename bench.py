@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """Throughput benchmark of the association hot path (driver contract: one JSON line on stdout).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4|cfg5]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload = BASELINE.json configs[3] / SURVEY §8d cfg4, the configuration the metric is quoted on:
-pp_pv_40e_dualadd_subabs_C (Fusion C, minus_abs, dual_add), N = M = 128 detections per frame,
-P = 512 LiDAR points per detection, 64x64 crops.  A "step" = one pass of forward + association LP
-over `--pairs` frame-pairs per GPU (weak scaling: per-GPU work fixed).  Frame-pairs are independent
-units, sharded over ranks with no data-path collective; the only collective is the final gather of
-the assignment indices, inside the timed region.
+Default workload = BASELINE.json configs[3] / SURVEY §8d cfg4, the configuration the metric is quoted on:
+pp_pv_40e_dualadd_subabs_C (Fusion C, minus_abs, dual_add), N = M = 128 detections per frame, P = 512 LiDAR points per
+detection, 64x64 crops.  A "step" = one pass of forward + association LP over `--pairs` frame-pairs per GPU (weak
+scaling: per-GPU work fixed; `--total-pairs T` fixes the total instead = strong scaling, BASELINE's "B=4096 sharded 8x").
+Frame-pairs are independent units, sharded over ranks with no data-path collective; the only collective is the final
+gather of the assignment indices (mmmot_b200.parallel.gather_pairs), inside the timed region.
+--config cfg2 / cfg3: BASELINE configs[1] / [2] (Fusion A N=32 B=64; Fusion C multiply/none N=64 P=512 B=256).
+--config cfg5: BASELINE configs[4], the N sweep 8 -> 256 of the affinity + LP kernels alone (value = the N=128 point).
 
-value : frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks).
-e2e   : same metric through the public API with HOST (pinned) inputs: H2D of crops/points and D2H
-        of the assignment results inside the timed region.
-roofline: dominant kernel = tma::gemm_tma_kernel in conv mode, the TMA-fed tcgen05 3x3-conv contraction of the
-        VGG trunk (12 launches per chunk, 83 % of the algorithmic FLOPs, ~50 % of the step), timed per launch
-        with CUDA events on the launching stream (library hook mmmot_timing_*).
-cpu_baseline / --impl reference: the oracle port of the reference's PyTorch-CPU path (the reference
-        is pure Python and /root/reference does not exist on the GPU box) on all host cores.
+value   : frame-pairs/s with inputs resident in HBM (CUDA events, max over ranks).
+e2e     : same metric through the public API with HOST (pinned) inputs: H2D of crops/points and D2H of the assignment
+          results inside the timed region.
+roofline: dominant kernel = the TMA-fed tcgen05 3x3-conv contraction of the VGG trunk (layers 1..12, 83 % of the
+          algorithmic FLOPs), timed per launch with CUDA events on the launching stream (library hook mmmot_timing_*).
+kernels : the same per-launch timing for EVERY hot kernel of the path, tagged (stage, layer): algorithmic FLOPs and
+          compulsory HBM bytes of the launch / its measured duration, against the measured tensor / HBM peak.
+cpu_baseline / --impl reference: the oracle port of the reference's PyTorch-CPU path (the reference is pure Python and
+          /root/reference does not exist on the GPU box) on the host cores (thread count swept on the real shape).
 """
 import argparse
 import ctypes
@@ -34,10 +37,37 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(fusion="C", affinity_op="minus_abs", softmax_mode="dual_add", neg_threshold=0.2, n=128, pts=512, hw=64)
-METRIC = "frame-pairs/sec at N=128 dets"
-# algorithmic FLOPs per frame-pair at cfg4: VGG 641.4 G, affinity 83.76 G, PointNet 48.8 G, total 775.7 G
-FLOP_PER_PAIR = 775.7e9
+CONFIGS = {
+    # name: model / shape of SURVEY §8d ("pairs" = frame-pairs per GPU per step)
+    "cfg2": dict(fusion="A", affinity_op="multiply", softmax_mode="none", neg_threshold=0.2, n=32, pts=128, hw=64, pairs=64,
+                 what="cfg2 pp_pv_40e_mul_A: Fusion A, multiply, no softmax, N=M=32 dets/frame, P=128 LiDAR pts/det, 64x64 crops"),
+    "cfg3": dict(fusion="C", affinity_op="multiply", softmax_mode="none", neg_threshold=0.2, n=64, pts=512, hw=64, pairs=256,
+                 what="cfg3 pp_pv_40e_mul_C: Fusion C, multiply, no softmax, N=M=64 dets/frame, P=512 LiDAR pts/det, 64x64 crops"),
+    "cfg4": dict(fusion="C", affinity_op="minus_abs", softmax_mode="dual_add", neg_threshold=0.2, n=128, pts=512, hw=64, pairs=128,
+                 what="cfg4 pp_pv_40e_dualadd_subabs_C: Fusion C, minus_abs, dual_add, N=M=128 dets/frame, P=512 LiDAR pts/det, "
+                      "64x64 crops"),
+    "cfg5": dict(fusion="C", affinity_op="minus_abs", softmax_mode="dual_add", neg_threshold=0.2, n=128, pts=0, hw=0, pairs=32,
+                 what="cfg5 N sweep 8..256 of the affinity + new/end + softmax + LP kernels alone (inputs = 3x512x2N feature stacks)"),
+}
+CFG = CONFIGS["cfg4"]          # tools/ import this
+SWEEP_N = (8, 16, 32, 64, 128, 256)
+
+
+def flop_per_pair(c):
+    """Algorithmic FLOPs per frame-pair, minimal work (no dead STN, split head)."""
+    n, L = c["n"], 2 * c["n"]
+    aff = 3 * n * n * 1.7042e6 + 3 * L * 0.655e6
+    if not c["hw"]:
+        return aff
+    vgg = L * 30.693e9 * (c["hw"] / 224.0) ** 2 + L * 0.41e6
+    pn = L * c["pts"] * 0.369e6 + L * 1.57e6
+    fus = L * (1.05e6 if c["fusion"] in "AB" else 2.10e6) + 3 * L * 0.787e6
+    return vgg + pn + fus + aff
+
+
+def bytes_in_per_pair(c):
+    L = 2 * c["n"]
+    return L * 3 * c["hw"] * c["hw"] * 4 + L * c["pts"] * 12 + (L + 1) * 8 if c["hw"] else 3 * 512 * L * 4
 
 
 def load_peaks():
@@ -80,81 +110,230 @@ class ClockSampler(threading.Thread):
                 "power_w": pw[len(pw) // 2] if pw else None}
 
 
-def pick_cpu_threads():
-    """torch's intra-op scaling on many-core hosts is poor for these shapes (128 threads were 14x slower
-    than 8 on the GPU box); time one small frame-pair at a few thread counts and keep the fastest."""
+# --------------------------------------------------------------------------------------- CPU legs (oracle port)
+def pick_cpu_threads(c):
+    """torch's intra-op scaling on many-core hosts is poor for these shapes (128 threads were 14x slower than 8 on the
+    GPU box), so the thread count is swept on the REAL shape: the dominant CPU stage of the workload (the VGG trunk on
+    the pair's 2N crops; the affinity MLP for cfg5) is timed at a few counts up to all host cores, fastest wins."""
     from mmmot_b200.synthetic import synthetic_pair, synthetic_state_dict
     from oracle import torch_ref
     ncpu = os.cpu_count() or 1
-    sd = synthetic_state_dict(CFG["fusion"], seed=0)
-    dets, info, split = synthetic_pair(16, 16, 64, CFG["hw"], seed=0)
-    best, best_t = 1, float("inf")
+    sd = synthetic_state_dict(c["fusion"], seed=0)
+    if c["hw"]:
+        dets, _, _ = synthetic_pair(c["n"], c["n"], 8, c["hw"], seed=0)
+        probe = lambda: torch_ref.appearance(sd, dets)
+    else:
+        f = torch.relu(torch.randn(3, 512, 2 * c["n"], generator=torch.Generator().manual_seed(0)))
+        probe = lambda: torch_ref.associate(sd, f[:, :, :c["n"]], f[:, :, c["n"]:], c["affinity_op"], c["softmax_mode"])
+    best, best_t, sweep = 1, float("inf"), {}
     for th in sorted({min(ncpu, t) for t in (8, 16, 32, 64, ncpu)}):
         torch.set_num_threads(th)
-        torch_ref.forward(sd, dets, info, split, CFG["fusion"], CFG["affinity_op"], CFG["softmax_mode"], CFG["neg_threshold"])
-        t = time.perf_counter()
-        torch_ref.forward(sd, dets, info, split, CFG["fusion"], CFG["affinity_op"], CFG["softmax_mode"], CFG["neg_threshold"])
-        dt = time.perf_counter() - t
+        with torch.no_grad():
+            t = time.perf_counter()
+            probe()
+            dt = time.perf_counter() - t
+        sweep[th] = round(dt, 3)
         if dt < best_t:
             best, best_t = th, dt
-    return best
+        if dt > 4 * best_t:
+            break
+    return best, sweep
 
 
-def oracle_pairs_per_s(n_pairs, threads, budget_s=150.0):
-    """The reference's CPU path (oracle port of TrackingNet.forward + HiGHS restatement of the LP).
-    Bounded sample: stops early once `budget_s` seconds of CPU work are spent (>= 1 pair is always timed)."""
+def oracle_pairs_per_s(c, n_pairs, threads, budget_s=60.0):
+    """The reference's CPU path (oracle port of TrackingNet.forward + HiGHS restatement of the LP; cfg5: associate +
+    LP only).  Bounded sample: stops early once `budget_s` seconds of CPU work are spent (>= 1 pair is always timed)."""
     from mmmot_b200.synthetic import synthetic_pair, synthetic_state_dict
     from oracle import lp_ref, torch_ref
     torch.set_num_threads(threads)
-    sd = synthetic_state_dict(CFG["fusion"], seed=0)
+    sd = synthetic_state_dict(c["fusion"], seed=0)
+    n = c["n"]
     t_tot = 0.0
     for p in range(n_pairs):
-        dets, info, split = synthetic_pair(CFG["n"], CFG["n"], CFG["pts"], CFG["hw"], seed=p)
-        t = time.perf_counter()
-        det, link, new, end, _ = torch_ref.forward(sd, dets, info, split, CFG["fusion"], CFG["affinity_op"],
-                                                   CFG["softmax_mode"], CFG["neg_threshold"])
-        lp_ref.milp_solve(det[2], [link[0][2:3]], new[2], end[2], [CFG["n"], CFG["n"]])
+        if c["hw"]:
+            dets, info, split = synthetic_pair(n, n, c["pts"], c["hw"], seed=p)
+            t = time.perf_counter()
+            det, link, new, end, _ = torch_ref.forward(sd, dets, info, split, c["fusion"], c["affinity_op"], c["softmax_mode"],
+                                                       c["neg_threshold"])
+            lp_ref.milp_solve(det[2], [link[0][2:3]], new[2], end[2], [n, n])
+        else:
+            f = torch.relu(torch.randn(3, 512, 2 * n, generator=torch.Generator().manual_seed(p)))
+            det = torch.rand(2 * n, generator=torch.Generator().manual_seed(p))
+            t = time.perf_counter()
+            with torch.no_grad():
+                link, new, end = torch_ref.associate(sd, f[:, :, :n], f[:, :, n:], c["affinity_op"], c["softmax_mode"])
+            z = torch.zeros(n)
+            lp_ref.milp_solve(det, [link[2]], torch.cat([z, new[2]]), torch.cat([end[2], z]), [n, n])
         t_tot += time.perf_counter() - t
         if t_tot > budget_s:
             n_pairs = p + 1
             break
-    return n_pairs / t_tot, t_tot
+    return n_pairs / t_tot, t_tot, n_pairs
 
 
-def config_dict(pairs, world):
-    return {"workload": "cfg4 pp_pv_40e_dualadd_subabs_C: Fusion C, minus_abs, dual_add, N=M=128 dets/frame, "
-                        "P=512 LiDAR pts/det, 64x64 crops; forward + association LP",
-            "pairs_per_gpu_per_step": pairs, "global_pairs_per_step": pairs * world,
-            "parallelism": f"frame-pair sharding x{world}, final gather only",
-            "l2_policy": "inputs larger than L2 (%.1f GB per GPU per step vs 126 MB L2)" % (pairs * 14.16e6 / 1e9)}
+def cpu_leg(c, n_pairs):
+    threads, sweep = pick_cpu_threads(c)
+    rate, secs, done = oracle_pairs_per_s(c, n_pairs, threads)
+    what = "forward + LP" if c["hw"] else "affinity stage + LP"
+    return {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+            "thread_sweep_s": sweep,
+            "sample": f"{done} frame-pair(s) of the same workload ({what}, {secs:.1f} s of CPU work): oracle port of the reference "
+                      "PyTorch-CPU path + HiGHS MILP restatement of ortools_solve (OR-tools absent); torch threads = the fastest "
+                      "of the sweep in thread_sweep_s (seconds of the dominant CPU stage on this shape per thread count)"}, secs, done
 
 
-def run_reference(args, rank, world):
+def config_dict(c, name, pairs, world, scaling):
+    d = {"workload": c["what"] + ("; forward + association LP" if c["hw"] else ""),
+         "config": name, "pairs_per_gpu_per_step": pairs, "global_pairs_per_step": pairs * world,
+         "parallelism": f"frame-pair sharding x{world}, final gather only", "scaling_mode": scaling,
+         "l2_policy": "inputs larger than L2 (%.2f GB per GPU per step vs 126 MB L2)" % (pairs * bytes_in_per_pair(c) / 1e9)}
+    return d
+
+
+def run_reference(args, c, name, rank):
     if rank != 0:
         return
-    threads = pick_cpu_threads()                          # fastest thread count on this host (<= all cores)
-    t0 = time.perf_counter()
-    rate, secs = oracle_pairs_per_s(max(args.steps, 1), threads)    # one frame-pair per "step"
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "frame-pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+    cpu, secs, done = cpu_leg(c, max(args.steps, 1))
+    line = {"impl": "reference", "metric": metric_name(c), "value": cpu["value"], "unit": "frame-pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_dict(1, 1), note="CPU: one frame-pair per step (bounded sample of the same workload)"),
-            "cpu_baseline": {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{max(args.steps, 1)} frame-pairs of the cfg4 shape, oracle port of the reference "
-                                       "PyTorch-CPU forward + HiGHS MILP restatement of ortools_solve (OR-tools absent)"},
-            "e2e": {"value": rate, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": dict(config_dict(c, name, 1, 1, "weak"), note="CPU: one frame-pair per step (bounded sample of the same workload)"),
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def metric_name(c):
+    return f"frame-pairs/sec at N={c['n']} dets" + ("" if c["hw"] else " (affinity + LP kernels only)")
+
+
+# --------------------------------------------------------------------------------------- per-kernel rooflines
+TENSOR_TAGS = ("vgg.conv", "pointnet.l2", "pointnet.l3", "pointnet.l4", "pointnet.l5", "pointnet.head", "affinity.l1",
+               "affinity.l2", "affinity.l3")
+
+
+def collect_tags(lib):
+    n = lib.mmmot_timing_tag_count()
+    ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+    cnt = (ctypes.c_long * n)()
+    rc = lib.mmmot_timing_collect_tags(ms, fl, by, cnt)
+    assert rc == 0, rc
+    return {lib.mmmot_timing_tag_name(t).decode(): (ms[t], fl[t], by[t], cnt[t]) for t in range(n) if cnt[t]}
+
+
+def kernel_table(tags, steps, peaks):
+    """One row per (stage, layer): algorithmic work of its launches / their measured duration vs the binding peak."""
+    tpeak, hpeak = peaks.get("bf16_tflops_sustained", 1400.0), peaks.get("hbm_gbs", 6650.0)
+    rows = []
+    for name, (ms, fl, by, cnt) in tags.items():
+        if ms <= 0:
+            continue
+        tf, gb = fl / ms / 1e9, by / ms / 1e6
+        bound = "latency" if name == "lp.assign" else ("tensor" if name.startswith(TENSOR_TAGS) and name != "vgg.conv0" else "hbm")
+        row = {"kernel": name, "launches_per_step": cnt / steps, "ms_per_step": ms / steps, "bound": bound,
+               "algorithmic_tflops": round(tf, 1), "algorithmic_gbs": round(gb, 1)}
+        if bound == "tensor":
+            row.update(frac=round(tf / tpeak, 3), mma_issue_frac=round(3 * tf / tpeak, 3))
+        elif bound == "hbm":
+            row.update(frac=round(gb / hpeak, 3))
+        rows.append(row)
+    return rows
+
+
+# --------------------------------------------------------------------------------------- cfg5: affinity + LP sweep
+def run_sweep(args, c, name, rank, world, local):
+    import mmmot_b200
+    from mmmot_b200 import _lib
+    from mmmot_b200.synthetic import synthetic_state_dict
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch="branch_cls", score_fusion_arch=c["fusion"],
+                                 affinity_op=c["affinity_op"], softmax_mode=c["softmax_mode"], neg_threshold=c["neg_threshold"],
+                                 test_mode=2, dropblock=0)
+    net.load_state_dict(synthetic_state_dict(c["fusion"], seed=0))
+    net.cuda(dev).eval()
+    peaks, how = load_peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    points, main = [], None
+    for n in SWEEP_N:
+        # batch sized so that one step is >= ~100 ms of device work and inputs exceed L2 where they can
+        B = args.pairs if args.pairs else max(16, min(4096, int(32 * (128 / n) ** 2)))
+        g = torch.Generator(device=dev).manual_seed(1234 + n)
+        feats = torch.relu(torch.randn(B, 3, 512, 2 * n, device=dev, generator=g))
+        det = torch.rand(B, 2 * n, device=dev, generator=g)
+        h_feats = torch.empty(feats.shape, dtype=torch.float32, pin_memory=True).copy_(feats)
+        h_match = torch.empty(B, n, dtype=torch.int32, pin_memory=True)
+        d_feats = torch.empty_like(feats)
+        zn = torch.zeros(B, n, device=dev)
+
+        def step(f):
+            link, new, end = net.associate_batch(f, n)
+            return mmmot_b200.solve_batch(det, link[:, 2], torch.cat([zn, new[:, 2]], 1), torch.cat([end[:, 2], zn], 1), n, n)
+
+        def step_e2e():
+            d_feats.copy_(h_feats, non_blocking=True)
+            r = step(d_feats)
+            h_match.copy_(r["match"], non_blocking=True)
+
+        def timed(fn, hooks):
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            torch.cuda.synchronize(dev)
+            l0 = lib.mmmot_launch_count()
+            if hooks:
+                lib.mmmot_timing_enable(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            lib.mmmot_timing_enable(0)
+            return e0.elapsed_time(e1), lib.mmmot_launch_count() - l0, (collect_tags(lib) if hooks else None)
+        ms, launches, tags = timed(lambda: step(feats), True)
+        ms2, _, _ = timed(step_e2e, False)
+        pt = {"n": n, "pairs_per_step": B, "value": B * args.steps / (ms / 1e3), "e2e": B * args.steps / (ms2 / 1e3),
+              "ms_per_step": ms / args.steps, "gpu_launches": int(launches),
+              "algorithmic_tflops": B * args.steps / (ms / 1e3) * flop_per_pair(dict(c, n=n)) / 1e12,
+              "kernels": kernel_table(tags, args.steps, peaks)}
+        points.append(pt)
+        if n == c["n"]:
+            main = (pt, ms, ms2, launches, tags, B, h_feats.numel() * 4, h_match.numel() * 4)
+    clocks = sampler.summary()
+    pt, ms, ms2, launches, tags, B, h2d, d2h = main
+    l1 = next(k for k in pt["kernels"] if k["kernel"].startswith("affinity.l1"))
+    cpu = None
+    if not args.no_cpu:
+        cpu, _, _ = cpu_leg(c, args.cpu_pairs)
+    line = {"metric": metric_name(c), "value": pt["value"], "unit": "frame-pairs/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": pt["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tcgen05 engine: FP16 hi/lo split operands, fp32 accumulate; LP in f64)",
+            "data": "synthetic", "config": config_dict(c, name, B, 1, "weak"), "clocks": clocks,
+            "e2e": {"value": pt["e2e"], "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms2 / args.steps},
+            "gpu_launches": pt["gpu_launches"], "algorithmic_tflops": pt["algorithmic_tflops"],
+            "roofline": {"bound": "tensor", "kernel": "gen::gemm_gen_kernel (affinity layer 1: pairwise operand generated in-kernel, "
+                                                      "512 -> 1024, FP16 hi/lo split: 3 MMAs per algorithmic MAC)",
+                         "achieved": l1["algorithmic_tflops"], "peak": peaks.get("bf16_tflops_sustained", 1400.0), "unit": "TFLOP/s",
+                         "frac": l1["frac"], "peak_source": f"{how} bf16_tflops_sustained", "traffic": None},
+            "kernels": pt["kernels"], "sweep": points, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- full forward + LP
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("MMMOT_BENCH_PAIRS", "128")),
-                    help="frame-pairs per GPU per step")
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("MMMOT_BENCH_PAIRS", "0")),
+                    help="frame-pairs per GPU per step (default: the config's own batch)")
+    ap.add_argument("--total-pairs", type=int, default=0, help="strong scaling: total frame-pairs per step, sharded over the ranks")
     ap.add_argument("--cpu-pairs", type=int, default=2, help="frame-pairs timed for cpu_baseline (rank 0)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kseg", type=int, default=-1, help="tcgen05 conv K-segment length in 32-chunks (0 = off; default: library default)")
@@ -164,13 +343,20 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    name = args.config
+    c = CONFIGS[name]
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, c, name, rank)
+        return
+    if name == "cfg5":
+        if rank == 0:
+            run_sweep(args, c, name, rank, world, local)
         return
 
     import mmmot_b200
     from mmmot_b200 import _lib
+    from mmmot_b200.parallel import gather_pairs, shard_range
     from mmmot_b200.synthetic import synthetic_state_dict
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -183,32 +369,47 @@ def main():
     if args.kseg >= 0:
         lib.mmmot_set_kseg(args.kseg)
 
-    n, pts, hw = CFG["n"], CFG["pts"], CFG["hw"]
-    L, B = 2 * n, args.pairs
-    net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch="branch_cls", score_fusion_arch=CFG["fusion"],
-                                 affinity_op=CFG["affinity_op"], softmax_mode=CFG["softmax_mode"],
-                                 neg_threshold=CFG["neg_threshold"], test_mode=2, dropblock=0)
-    net.load_state_dict(synthetic_state_dict(CFG["fusion"], seed=0))
+    n, pts, hw = c["n"], c["pts"], c["hw"]
+    L = 2 * n
+    if args.total_pairs:
+        scaling, total = "strong", args.total_pairs
+        lo, hi = shard_range(total, rank, world)
+        B = hi - lo
+    else:
+        scaling, B = "weak", (args.pairs or c["pairs"])
+        total = B * world
+    net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch="branch_cls", score_fusion_arch=c["fusion"],
+                                 affinity_op=c["affinity_op"], softmax_mode=c["softmax_mode"],
+                                 neg_threshold=c["neg_threshold"], test_mode=2, dropblock=0)
+    net.load_state_dict(synthetic_state_dict(c["fusion"], seed=0))
     net.cuda(dev).eval()
 
-    # synthetic inputs of the cfg4 shape, generated on the device (seeded per rank), mirrored to pinned host memory
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    crops = torch.randn(B * L, 3, hw, hw, device=dev, generator=g)
-    centre = torch.rand(B * L, 1, 3, device=dev, generator=g) * torch.tensor([60.0, 40.0, 2.0], device=dev) + \
-        torch.tensor([0.0, -20.0, -2.0], device=dev)
-    points = (torch.randn(B * L, pts, 3, device=dev, generator=g) * torch.tensor([2.0, 1.0, 0.8], device=dev) + centre).reshape(-1, 3)
-    split = torch.arange(0, B * L * pts + 1, pts, dtype=torch.int32)
+    def make_inputs(seed_rank, pairs):
+        """synthetic inputs of the config's shape, generated on the device (seeded per rank)"""
+        g = torch.Generator(device=dev).manual_seed(1234 + seed_rank)
+        crops = torch.randn(pairs * L, 3, hw, hw, device=dev, generator=g)
+        centre = torch.rand(pairs * L, 1, 3, device=dev, generator=g) * torch.tensor([60.0, 40.0, 2.0], device=dev) + \
+            torch.tensor([0.0, -20.0, -2.0], device=dev)
+        points = (torch.randn(pairs * L, pts, 3, device=dev, generator=g) * torch.tensor([2.0, 1.0, 0.8], device=dev) + centre).reshape(-1, 3)
+        return crops, points, torch.arange(0, pairs * L * pts + 1, pts, dtype=torch.int32)
+    crops, points, split = make_inputs(rank, B)
+    # mirrored to pinned host memory for the end-to-end leg
     h_crops = torch.empty(crops.shape, dtype=torch.float32, pin_memory=True).copy_(crops)
     h_points = torch.empty(points.shape, dtype=torch.float32, pin_memory=True).copy_(points)
     h_match = torch.empty(B, n, dtype=torch.int32, pin_memory=True)
     h_flags = torch.empty(3, B, L, dtype=torch.float32, pin_memory=True)
+    h_status = torch.zeros(8, dtype=torch.int32, pin_memory=True)
     d_crops2, d_points2 = torch.empty_like(crops), torch.empty_like(points)
 
+    last = {}
+
     def step_resident():
-        o = net.predict_batch(crops, points, split, n)
+        o = net.predict_batch(crops, points, split, n, check=False)
         if world > 1:
-            gathered = [torch.empty_like(o["match"]) for _ in range(world)]
-            dist.all_gather(gathered, o["match"])
+            last["match"] = gather_pairs(o["match"], total)      # the path's only collective (SURVEY §8e)
+        else:
+            last["match"] = o["match"]
+        last["status"] = o["status"]
         return o
 
     # e2e: pinned host -> device copies are pipelined against compute in sub-batches (copy stream + events);
@@ -235,18 +436,17 @@ def main():
         for i in range(nsub):
             c0, c1 = i * sb * L, (i + 1) * sb * L
             cur.wait_event(ev_copied[i])
-            o = net.predict_batch(d_crops2[c0:c1], d_points2[c0 * pts:c1 * pts], sub_split, n)
+            o = net.predict_batch(d_crops2[c0:c1], d_points2[c0 * pts:c1 * pts], sub_split, n, check=False)
             ev_used[i].record(cur)
             p0, p1 = i * sb, (i + 1) * sb
             h_match[p0:p1].copy_(o["match"], non_blocking=True)
             h_flags[0, p0:p1].copy_(o["assign_det"], non_blocking=True)
             h_flags[1, p0:p1].copy_(o["assign_new"], non_blocking=True)
             h_flags[2, p0:p1].copy_(o["assign_end"], non_blocking=True)
+            h_status[i:i + 1].copy_(o["status"], non_blocking=True)     # the library's range flag travels with the results
             outs.append(o["match"])
         if world > 1:
-            allm = torch.cat(outs, 0)
-            gathered = [torch.empty_like(allm) for _ in range(world)]
-            dist.all_gather(gathered, allm)
+            gather_pairs(torch.cat(outs, 0), total)
         return outs
 
     def timed(fn, steps, warmup, with_hooks=False):
@@ -269,46 +469,63 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
-        hook = None
+        tags = None
         if with_hooks:
             lib.mmmot_timing_enable(0)
-            tm, fl, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
-            lib.mmmot_timing_collect(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(cnt))
-            hook = (tm.value, fl.value, cnt.value)
+            tags = collect_tags(lib)
         launches = lib.mmmot_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms, launches, hook
+        return ms, launches, tags
 
+    warm = max(args.warmup, 3)            # timing rule: >= 3 warm-up steps
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, hook = timed(step_resident, args.steps, args.warmup, with_hooks=True)
+    ms, launches, tags = timed(step_resident, args.steps, warm, with_hooks=True)
     clocks = sampler.summary() if sampler else None
+    status = int(last["status"])
     sampler2 = ClockSampler(local) if rank == 0 else None
     if sampler2:
         sampler2.start()
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
+    ms_e2e, _, _ = timed(step_e2e, args.steps, warm)
     clocks_e2e = sampler2.summary() if sampler2 else None
+    status |= int(h_status.max())
+
+    # N-GPU result == 1-GPU result: rank 0 recomputes rank 1's shard from the same seeded inputs and compares it bit
+    # for bit with what the gather returned (outside the timed region)
+    shard_equal = None
+    if world > 1 and rank == 0:
+        if scaling == "strong":
+            l1, h1 = shard_range(total, 1, world)
+        else:
+            l1, h1 = B, 2 * B
+        c1, p1, s1 = make_inputs(1, h1 - l1)
+        o1 = net.predict_batch(c1, p1, s1, n)
+        shard_equal = bool(torch.equal(o1["match"], last["match"][l1:h1]))
 
     if rank == 0:
         peaks, how = load_peaks()
-        value = B * world * args.steps / (ms / 1e3)
-        e2e = B * world * args.steps / (ms_e2e / 1e3)
-        conv_ms, conv_flop, conv_n = hook
+        value = total * args.steps / (ms / 1e3)
+        e2e = total * args.steps / (ms_e2e / 1e3)
+        conv = [v for k, v in tags.items() if k.startswith("vgg.conv") and k != "vgg.conv0"]
+        conv_ms, conv_flop, conv_n = sum(v[0] for v in conv), sum(v[1] for v in conv), sum(v[3] for v in conv)
         achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         tc_engine = args.engine != "fp32"
-        traffic = None
-        try:    # dram bytes per frame-pair of the 12 conv launches, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
-                tr = json.load(f)
-            if tc_engine:
-                traffic = tr["dram_bytes_per_pair"] * (B / max(conv_n / (12 * args.steps), 1)) / 12
-        except Exception:
-            pass
+        traffic, traffic_note = None, None
+        for f in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+            try:    # dram bytes per frame-pair of the 12 conv launches, from a committed ncu --set full capture of cfg4
+                with open(os.path.join(ROOT, "profiles", f)) as fh:
+                    tr = json.load(fh)
+                if tc_engine and name == "cfg4":
+                    traffic = tr["dram_bytes_per_pair"] * (B * args.steps * 12 / max(conv_n, 1)) / 12
+                    traffic_note = f"avg dram bytes per launch, scaled from profiles/{f} (ncu --set full, dram__bytes_read+write)"
+                break
+            except Exception:
+                continue
         roofline = {"bound": "tensor",
                     "kernel": ("tma::gemm_tma_kernel / gemm_tma_px_kernel, conv mode (TMA-fed tcgen05 3x3-conv contraction of the VGG "
                                "trunk, layers 1..12, FP16 hi/lo split: 3 MMAs per algorithmic MAC)") if tc_engine else
@@ -319,26 +536,26 @@ def main():
                     "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step); 'achieved' counts "
                                    "ALGORITHMIC FLOPs (2*Cout*9Cin*pixels per launch); the tensor pipe executes 3x that",
                     "launches_timed": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
-                    "share_of_step": conv_ms / ms, "traffic": traffic,
-                    "traffic_note": "avg dram bytes per launch, scaled from profiles/r01_conv_traffic.json (ncu --set full)"}
+                    "share_of_step": conv_ms / ms, "traffic": traffic, "traffic_note": traffic_note}
         cpu = None
         if not args.no_cpu and world == 1:      # the CPU baseline is reported at N=1 only
-            threads = pick_cpu_threads()
-            rate, secs = oracle_pairs_per_s(args.cpu_pairs, threads)
-            cpu = {"value": rate, "unit": "frame-pairs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-                   "sample": f"{args.cpu_pairs} frame-pairs of the same cfg4 workload ({secs:.1f} s), oracle port of the reference "
-                             "PyTorch-CPU forward + HiGHS restatement of the LP"}
+            cpu, _, _ = cpu_leg(c, args.cpu_pairs)
         h2d = h_crops.numel() * 4 + h_points.numel() * 4 + split.numel() * 4
-        d2h = h_match.numel() * 4 + h_flags.numel() * 4
-        line = {"metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (tcgen05 engine: FP16 hi/lo split operands, fp32 accumulate)" if args.engine != "fp32" else "f32", "data": "synthetic", "config": dict(config_dict(B, world), engine=args.engine),
+        d2h = h_match.numel() * 4 + h_flags.numel() * 4 + nsub * 4
+        line = {"metric": metric_name(c), "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None,
+                "dtype": "f32 (tcgen05 engine: FP16 hi/lo split operands, fp32 accumulate)" if tc_engine else "f32",
+                "data": "synthetic", "config": dict(config_dict(c, name, B, world, scaling), engine=args.engine),
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "e2e": {"value": e2e, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches),
-                "algorithmic_tflops": value * FLOP_PER_PAIR / 1e12 / world,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "range_status": status,
+                "algorithmic_tflops": value * flop_per_pair(c) / 1e12 / world,
+                "roofline": roofline, "kernels": kernel_table(tags, args.steps, peaks), "cpu_baseline": cpu}
+        if world > 1:
+            line["shard_equal"] = shard_equal
+        assert status == 0, "MMMOT_E_RANGE raised during the benchmark"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -41,13 +41,20 @@ struct GenP {
   int* status;         // workspace status word (FP16 range flag) or null
 };
 
+__device__ __forceinline__ void lds128(uint32_t addr, float4& v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+}
 __device__ __forceinline__ void ld_global_256(const float* p, float (&v)[8]) {
   asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "l"(p));
 }
 
-template <int GEN>
+// PAIRED: software-pipelined producers (the next chunk's source vectors are loaded before the current chunk is
+// converted).  GEN_PAIR_*: only for m == 128, where a 256-column tile is two whole rows i and the thread's four items are
+// {row i0, row i0 + 1} x {j = cb, j = cb + 64}: 2 + 2 source vectors instead of 4 + 4, which leaves the registers.
+// GEN_NORM: any shape; the GroupNorm affine is then re-read from shared memory per pair of items.
+template <int GEN, bool PAIRED>
 static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const GenP P) {
   const GemmP& p = P.t.g;
   extern __shared__ uint8_t smem_raw[];
@@ -216,17 +223,23 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
     __syncwarp();
   } else {
     // =============================== OPERAND PRODUCERS ===============================
-    // thread = (k group kg of 8, four columns cb + 64 r).  Per chunk: the 256-bit source loads of the four items are
-    // issued BEFORE waiting for the ring slot to drain (latency overlaps the wait); then every item is converted,
-    // split into FP16 hi/lo and written as one 16-byte piece per plane of the canonical K-major layout:
+    // thread = (k group kg of 8, four columns cb + 64 r).  Per chunk every item is converted, split into FP16 hi/lo
+    // and written as one 16-byte piece per plane of the canonical K-major layout:
     //   byte offset = kg * B_LBO + (column / 8) * 128 + (column % 8) * 16
     // (a quarter warp = one kg, eight consecutive columns -> 128 contiguous bytes: conflict-free).
+    // The 256-bit source loads of chunk c+1 are issued before chunk c is converted (two register sets, ping-pong), so
+    // the L2 transfer of one chunk overlaps the conversion of the previous one; the generic pairwise variant (8 source
+    // vectors per chunk) has no registers for that and only overlaps its loads with the wait for the ring slot.
+    constexpr bool PREFETCH = PAIRED;
+    constexpr int NA = (GEN == GEN_NORM || !PAIRED) ? 4 : 2;       // source vectors of 8 floats per chunk: a / y ...
+    constexpr int NB = GEN == GEN_NORM ? 0 : (PAIRED ? 2 : 4);     // ... and b
     const int pt = tid - G_PROD_WARP0 * 32;   // 0..255
     const int kg = (pt >> 3) & 3;
     const int cb = (pt & 7) + 8 * (pt >> 5);
     const uint32_t off0 = (uint32_t)kg * B_LBO + (uint32_t)(cb >> 3) * 128u + (uint32_t)(cb & 7) * 16u;   // + r * 1024
     uint32_t it = 0, racc = 0;
     int g_staged = -1;
+    struct Raw { float a[NA][8]; float b[NB ? NB : 1][8]; };
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = (int)(t / mgroups);
       int g, c0, len;
@@ -234,7 +247,7 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
       unsigned okmask = 0;
       // 32-bit element offsets of the items' rows (this thread's k group) relative to the tile's / group's base
       const float* tbase = GEN == GEN_NORM ? P.src + ((long)g * p.x_gs + c0) * P.ld_src : P.src + (long)g * P.Lf * p.K;
-      int oa[4], ob[GEN == GEN_NORM ? 1 : 4];
+      int oa[NA], ob[NB ? NB : 1];
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int col = cb + 64 * r;
@@ -245,8 +258,13 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
         } else {
           const int s = c0 + cc;
           const int i = s / P.m, j = s - i * P.m;
-          oa[r] = i * p.K + kg * 8;
-          ob[r] = (P.n + j) * p.K + kg * 8;
+          if (!PAIRED) {
+            oa[r] = i * p.K + kg * 8;
+            ob[r] = (P.n + j) * p.K + kg * 8;
+          } else {
+            if (!(r & 1)) oa[r >> 1] = i * p.K + kg * 8;          // r = 0, 2: the two rows i
+            if (r < 2) ob[r] = (P.n + j) * p.K + kg * 8;          // r = 0, 1: the two detections j
+          }
         }
       }
       if (GEN == GEN_NORM && g != g_staged) {   // same decision in every producer thread: stage the group's affine
@@ -258,41 +276,41 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
         asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");
         g_staged = g;
       }
-      for (int kc = 0; kc < KC; kc++, it++) {
-        const int s = it % STAGES;
-        float va[4][8], vb[GEN == GEN_NORM ? 1 : 4][8];
-        if (!(P.t.dbg & 4)) {
+      auto load = [&](Raw& R, int kc) {
+        if (P.t.dbg & 4) return;
 #pragma unroll
-          for (int r = 0; r < 4; r++) {
-            ld_global_256(tbase + oa[r] + kc * BK, va[r]);
-            if (GEN != GEN_NORM) ld_global_256(tbase + ob[r] + kc * BK, vb[r]);
-          }
-        }
+        for (int r = 0; r < NA; r++) ld_global_256(tbase + oa[r] + kc * BK, R.a[r]);
+#pragma unroll
+        for (int r = 0; r < NB; r++) ld_global_256(tbase + ob[r] + kc * BK, R.b[r]);
+      };
+      // wait for the ring slot, convert + store the chunk, publish it
+      auto emit = [&](const Raw& R, int kc) {
+        const int s = it % STAGES;
         mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1u);
         uint8_t* bh = sm + s * STAGE_BYTES + 2 * A_SUB + off0;
         if (!(P.t.dbg & 4)) {
+          const uint32_t sca = smem_u32(s_gsc + kc * BK + kg * 8), sha = smem_u32(s_gsh + kc * BK + kg * 8);
           float4 sc0, sc1, sh0, sh1;
-          if (GEN == GEN_NORM) {
-            sc0 = *reinterpret_cast<const float4*>(s_gsc + kc * BK + kg * 8);
-            sc1 = *reinterpret_cast<const float4*>(s_gsc + kc * BK + kg * 8 + 4);
-            sh0 = *reinterpret_cast<const float4*>(s_gsh + kc * BK + kg * 8);
-            sh1 = *reinterpret_cast<const float4*>(s_gsh + kc * BK + kg * 8 + 4);
-          }
 #pragma unroll
           for (int r = 0; r < 4; r++) {
             float x[8];
             if (GEN == GEN_NORM) {
-              x[0] = fmaxf(fmaf(va[r][0], sc0.x, sh0.x), 0.f); x[1] = fmaxf(fmaf(va[r][1], sc0.y, sh0.y), 0.f);
-              x[2] = fmaxf(fmaf(va[r][2], sc0.z, sh0.z), 0.f); x[3] = fmaxf(fmaf(va[r][3], sc0.w, sh0.w), 0.f);
-              x[4] = fmaxf(fmaf(va[r][4], sc1.x, sh1.x), 0.f); x[5] = fmaxf(fmaf(va[r][5], sc1.y, sh1.y), 0.f);
-              x[6] = fmaxf(fmaf(va[r][6], sc1.z, sh1.z), 0.f); x[7] = fmaxf(fmaf(va[r][7], sc1.w, sh1.w), 0.f);
+              const float(&y)[8] = R.a[r];
+              // prefetching variant: the affine is re-read from shared memory per pair of items (volatile asm) instead
+              // of holding the eight (scale, shift) pairs across the chunk: 16 registers for the prefetched vectors
+              if (!PAIRED ? r == 0 : !(r & 1)) { lds128(sca, sc0); lds128(sca + 16, sc1); lds128(sha, sh0); lds128(sha + 16, sh1); }
+              x[0] = fmaxf(fmaf(y[0], sc0.x, sh0.x), 0.f); x[1] = fmaxf(fmaf(y[1], sc0.y, sh0.y), 0.f);
+              x[2] = fmaxf(fmaf(y[2], sc0.z, sh0.z), 0.f); x[3] = fmaxf(fmaf(y[3], sc0.w, sh0.w), 0.f);
+              x[4] = fmaxf(fmaf(y[4], sc1.x, sh1.x), 0.f); x[5] = fmaxf(fmaf(y[5], sc1.y, sh1.y), 0.f);
+              x[6] = fmaxf(fmaf(y[6], sc1.z, sh1.z), 0.f); x[7] = fmaxf(fmaf(y[7], sc1.w, sh1.w), 0.f);
             } else {
+              const float(&av)[8] = R.a[PAIRED ? (r >> 1) : r];
+              const float(&bv)[8] = R.b[NB ? (PAIRED ? (r & 1) : r) : 0];
 #pragma unroll
               for (int e = 0; e < 8; e++) {
-                const int rb = GEN == GEN_NORM ? 0 : r;
-                if (GEN == GEN_PAIR_MUL) x[e] = va[r][e] * vb[rb][e];
-                else if (GEN == GEN_PAIR_ABS) x[e] = fabsf((va[r][e] - vb[rb][e]) * 0.5f);
-                else x[e] = (va[r][e] - vb[rb][e]) * 0.5f;
+                if (GEN == GEN_PAIR_MUL) x[e] = av[e] * bv[e];
+                else if (GEN == GEN_PAIR_ABS) x[e] = fabsf((av[e] - bv[e]) * 0.5f);
+                else x[e] = (av[e] - bv[e]) * 0.5f;
               }
             }
             uint32_t h[4], l[4];
@@ -309,6 +327,25 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
         fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(s));
+        it++;
+      };
+      if (PREFETCH) {
+        Raw R0, R1;
+        load(R0, 0);
+        for (int kc = 0; kc < KC; kc += 2) {
+          if (kc + 1 < KC) load(R1, kc + 1);
+          emit(R0, kc);
+          if (kc + 1 < KC) {
+            if (kc + 2 < KC) load(R0, kc + 2);
+            emit(R1, kc + 1);
+          }
+        }
+      } else {
+        for (int kc = 0; kc < KC; kc++) {
+          Raw R;
+          load(R, kc);
+          emit(R, kc);
+        }
       }
     }
     mm_range_flag2(P.status, racc);
@@ -328,15 +365,15 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
 // tiling, 256 columns per tile), x_gs (NORM: source rows per group), Y / y_gs / y_ms = fp32 channels-last output (or
 // null), part = two GroupNorm partials per tile (stats_reduce(..., mult = 2)).  Wp = weights packed by
 // weights.py::pack_tc.  PAIR: src = fcl [G][Lf][K]; NORM: src = [G*x_gs][ld_src] fp32, gsc/gsh [G][K].
-template <int GEN>
-static int gemm_gen_launch(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
+template <int GEN, bool PAIRED>
+static int gemm_gen_launch_t(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
                            const float* gsc, const float* gsh, int n, int m, int Lf, int* status, cudaStream_t st) {
   if (!Wp || !src || g.num_tiles <= 0 || g.K % tc::BK || g.tile_tab) return MMMOT_E_ARG;
   if (GEN == gen::GEN_NORM && (g.K > gen::G_MAX_K || !gsc || !gsh || ld_src < g.K || (ld_src & 7))) return MMMOT_E_ARG;
   int sms = 0;
   MM_TRY(mm_sm_count(&sms));
   static std::atomic<unsigned long long> attr{0};
-  MM_TRY(mm_ensure_smem(gen::gemm_gen_kernel<GEN>, gen::G_SMEM_BYTES, attr));
+  MM_TRY(mm_ensure_smem(gen::gemm_gen_kernel<GEN, PAIRED>, gen::G_SMEM_BYTES, attr));
   gen::GenP P;
   memset(&P, 0, sizeof(P));
   P.t.g = g;
@@ -353,7 +390,16 @@ static int gemm_gen_launch(const GemmP& g, const uint4* Wp, float out_scale, con
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);
-  gen::gemm_gen_kernel<GEN><<<grid, gen::G_THREADS, gen::G_SMEM_BYTES, st>>>(P);
+  gen::gemm_gen_kernel<GEN, PAIRED><<<grid, gen::G_THREADS, gen::G_SMEM_BYTES, st>>>(P);
   MM_LAUNCH_CHECK();
   return 0;
+}
+
+template <int GEN>
+static int gemm_gen_launch(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
+                           const float* gsc, const float* gsh, int n, int m, int Lf, int* status, cudaStream_t st) {
+  // debug bit 10 (1024): producers without the software pipeline (A/B runs)
+  const bool pipe = !(mm_debug_flags() & 1024) && (GEN == gen::GEN_NORM ? (mm_debug_flags() & 4096) != 0 : m == 128);
+  if (pipe) return gemm_gen_launch_t<GEN, true>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, status, st);
+  return gemm_gen_launch_t<GEN, false>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, status, st);
 }
