@@ -338,8 +338,10 @@ def test_full_forward_at_baseline_config(name, fusion, op, sm, n, pts, hw):
     (rdet, rlink, rnew, rend, _), st = torch_ref.forward(sd, dets, info, split, fusion, op, sm, 0.2, return_stages=True)
     o = net.forward_batch(dets.cuda(), info["points"][0].cuda(), info["points_split"][0], n, n, keep_feats=True)
     rep = []
-    for s_ in range(3):
-        check_close(o["feats"][0, s_], st["feats"][s_], TOL, f"{name} feats[{s_}]", rep, max_outside=ELEM_OUTSIDE)
+    for s_ in range(3):     # intermediate feature stacks: max-norm metric (GroupNorm outputs cross zero, so a bound relative to
+        e = relerr(o["feats"][0, s_], st["feats"][s_])          # each element's own magnitude is meaningless there)
+        rep.append((f"{name} feats[{s_}]", e))
+        assert e < TOL, rep[-1]
     check_close(o["link"][0], rlink[0], TOL, f"{name} link", rep, max_outside=ELEM_OUTSIDE)
     check_close(o["new"][0], rnew[:, n:], TOL, f"{name} new", rep, max_outside=ELEM_OUTSIDE)
     check_close(o["end"][0], rend[:, :n], TOL, f"{name} end", rep, max_outside=ELEM_OUTSIDE)
