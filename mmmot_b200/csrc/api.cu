@@ -183,7 +183,7 @@ extern "C" int mmmot_debug_linear_gen(const void* Wp, float wp_scale, const floa
   p.S = S; p.tiles_per_group = mm_cdiv(S, tc::BN); p.num_tiles = p.tiles_per_group;
   p.x_gs = S;
   p.Y = Y; p.y_gs = S; p.y_ms = M;
-  return gemm_gen_launch<gen::GEN_NORM>(p, (const uint4*)Wp, wp_scale, X, K, sc, sh, 0, 0, 0, nullptr, (cudaStream_t)stream);
+  return gemm_gen_launch<gen::GEN_NORM>(p, (const uint4*)Wp, wp_scale, X, K, sc, sh, 0, 0, 0, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

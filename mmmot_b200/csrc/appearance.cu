@@ -95,6 +95,12 @@ __global__ void plane_mean_planar_kernel(const __half* __restrict__ in, float* _
   out[idx] = s / (float)hw;
 }
 
+// pooled[img][c] = sum[img][c] * 2^-32 / hw : the fixed-point per-image sums of the fused pool epilogue -> SkipPool's average
+__global__ void pool_sum_mean_kernel(const unsigned long long* __restrict__ sum, float* __restrict__ out, long n, float inv_hw) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = (float)((double)sum[idx] * (1.0 / 4294967296.0) * (double)inv_hw);
+}
+
 // First VGG layer (3 -> 64, K = 27) of the tensor-core trunk: too thin for the MMA path (memory-bound: 1 MB of
 // output per crop), so a direct FP32 FFMA kernel writes the FP16 hi/lo NHWC planes the next layer's TMA loads
 // read.  Each thread: 2 horizontally adjacent pixels x 16 channels (weights from smem as 128-bit loads);
@@ -269,6 +275,7 @@ extern "C" size_t mmmot_appearance_workspace(int n_img, int H, int W) {
   a.take<float>(act);
   for (int s = 0; s < 4; s++) a.take<float>((size_t)n_img * kSkipC[s]);
   a.take<float>((size_t)(n_img + 16) * H * W * 16);   // K-segment partial sums, tile order (largest: 256 ch at H/4 x W/4)
+  a.take<unsigned long long>((size_t)n_img * 512);     // per-image sums of a pooled skip map (fused pool epilogue)
   return a.off;
 }
 
@@ -284,6 +291,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
   float* pooled[4];
   for (int s = 0; s < 4; s++) pooled[s] = ar.take<float>((size_t)n_img * kSkipC[s]);
   float* kseg_scratch = ar.take<float>((size_t)(n_img + 16) * H * W * 16);
+  unsigned long long* pool_sum = ar.take<unsigned long long>((size_t)n_img * 512);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
 
   // Tensor-core trunk: activations live as FP16 hi/lo NHWC planes between layers; the epilogue of one conv
@@ -329,10 +337,14 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
         p.bias = wts->w[MMMOT_W_VGG_B0 + i];
         p.M = cout;
         p.relu = 1;
-        // a pooled layer asks for the 2x2 max-pool to be fused into the epilogue (64-channel layers can)
+        // a pooled layer asks for the 2x2 max-pool to be fused into the epilogue; a skip map's global average (SkipPool)
+        // rides along as per-image fixed-point sums
+        const bool skip_layer = kPoolAfter[i] && kSkipAfter[i] >= 0;
+        if (skip_layer) MM_CUDA(cudaMemsetAsync(pool_sum, 0, (size_t)n_img * cout * sizeof(unsigned long long), st));
         MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
                                     cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch,
-                                    kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue, status));
+                                    kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue, status,
+                                    skip_layer ? pool_sum : nullptr));
       }
       if (timed) mm_timing_end(st);
       cur = hb[which]; cur_plane = plane_out; which ^= 1;
@@ -349,7 +361,11 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
           cur = hb[which]; cur_plane = plane_p; which ^= 1;
         }
         int s = kSkipAfter[i];
-        if (s >= 0) {
+        if (s >= 0 && pooled_in_epilogue && i > 1) {
+          const long nn = (long)n_img * kSkipC[s];
+          pool_sum_mean_kernel<<<mm_cdiv(nn, 256), 256, 0, st>>>(pool_sum, pooled[s], nn, 1.0f / (float)(h * w));
+          MM_LAUNCH_CHECK();
+        } else if (s >= 0) {
           plane_mean_planar_kernel<<<mm_cdiv((long)n_img * kSkipC[s], 128), 128, 0, st>>>(cur, pooled[s], n_img, h * w,
                                                                                          kSkipC[s], cur_plane);
           MM_LAUNCH_CHECK();

@@ -38,7 +38,9 @@ struct GenP {
   const float* gsc;    // NORM: GroupNorm affine of the SOURCE layer, [G][K]
   const float* gsh;
   int n, m, Lf;        // PAIR: columns s = i*m + j, objs = feature rows [0, n), dets = [n, n + m), Lf = n + m
-  int* status;         // workspace status word (FP16 range flag) or null
+  // FP16 range: the producers do not track the magnitudes they convert (their instruction stream is the kernel's
+  // bottleneck); the callers bound the operand instead — PAIR: feats_cl_check_kernel on the feature stacks, NORM:
+  // gn_finalize's bound sqrt(count)*|gamma| + |beta| on the normalised values (both raise the status flag).
 };
 
 __device__ __forceinline__ void lds128(uint32_t addr, float4& v) {
@@ -99,7 +101,9 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
   const uint32_t tmem_base = *tmem_slot;
 
   // column tile -> group / first column / valid length
+  // (table tiling: {group, first ABSOLUTE row, length}; x_gs and y_gs are 0 then)
   auto tile_cols = [&](int nt, int& g, int& c0, int& len) {
+    if (p.tile_tab) { const int4 tt = p.tile_tab[nt]; g = tt.x; c0 = tt.y; len = tt.z; return; }
     g = nt / p.tiles_per_group;
     c0 = (nt - g * p.tiles_per_group) * BN;
     len = min(BN, p.S - c0);
@@ -237,7 +241,7 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
     const int kg = (pt >> 3) & 3;
     const int cb = (pt & 7) + 8 * (pt >> 5);
     const uint32_t off0 = (uint32_t)kg * B_LBO + (uint32_t)(cb >> 3) * 128u + (uint32_t)(cb & 7) * 16u;   // + r * 1024
-    uint32_t it = 0, racc = 0;
+    uint32_t it = 0;
     int g_staged = -1;
     struct Raw { float a[NA][8]; float b[NB ? NB : 1][8]; };
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -309,16 +313,13 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
 #pragma unroll
               for (int e = 0; e < 8; e++) {
                 if (GEN == GEN_PAIR_MUL) x[e] = av[e] * bv[e];
-                else if (GEN == GEN_PAIR_ABS) x[e] = fabsf((av[e] - bv[e]) * 0.5f);
+                else if (GEN == GEN_PAIR_ABS) x[e] = fabsf(av[e] - bv[e]) * 0.5f;   // == |(a - b) / 2| exactly; |.| folds into the FMUL
                 else x[e] = (av[e] - bv[e]) * 0.5f;
               }
             }
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              split_f16x2(x[2 * q], x[2 * q + 1], h[q], l[q]);
-              mm_range_track2(racc, h[q]);
-            }
+            for (int q = 0; q < 4; q++) split_f16x2(x[2 * q], x[2 * q + 1], h[q], l[q]);
             if (!((okmask >> r) & 1u)) { h[0] = h[1] = h[2] = h[3] = 0u; l[0] = l[1] = l[2] = l[3] = 0u; }   // beyond the group
             *reinterpret_cast<uint4*>(bh + r * 1024) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(bh + B_HALF + r * 1024) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -348,7 +349,6 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
         }
       }
     }
-    mm_range_flag2(P.status, racc);
   }
 
   // ---- teardown ----
@@ -362,13 +362,14 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
 }  // namespace gen
 
 // Host launcher.  g: M, K (multiple of 32, <= 512 for GEN_NORM), bias, S / tiles_per_group / num_tiles (uniform column
-// tiling, 256 columns per tile), x_gs (NORM: source rows per group), Y / y_gs / y_ms = fp32 channels-last output (or
+// tiling, 256 columns per tile) or tile_tab (GEN_NORM: ragged groups, absolute rows), x_gs (NORM: source rows per group), Y / y_gs / y_ms = fp32 channels-last output (or
 // null), part = two GroupNorm partials per tile (stats_reduce(..., mult = 2)).  Wp = weights packed by
 // weights.py::pack_tc.  PAIR: src = fcl [G][Lf][K]; NORM: src = [G*x_gs][ld_src] fp32, gsc/gsh [G][K].
 template <int GEN, bool PAIRED>
 static int gemm_gen_launch_t(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
-                           const float* gsc, const float* gsh, int n, int m, int Lf, int* status, cudaStream_t st) {
-  if (!Wp || !src || g.num_tiles <= 0 || g.K % tc::BK || g.tile_tab) return MMMOT_E_ARG;
+                           const float* gsc, const float* gsh, int n, int m, int Lf, cudaStream_t st) {
+  if (!Wp || !src || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
+  if (g.tile_tab && (GEN != gen::GEN_NORM || g.x_gs || g.y_gs)) return MMMOT_E_ARG;
   if (GEN == gen::GEN_NORM && (g.K > gen::G_MAX_K || !gsc || !gsh || ld_src < g.K || (ld_src & 7))) return MMMOT_E_ARG;
   int sms = 0;
   MM_TRY(mm_sm_count(&sms));
@@ -386,7 +387,6 @@ static int gemm_gen_launch_t(const GemmP& g, const uint4* Wp, float out_scale, c
   P.t.dbg = mm_debug_flags();
   P.src = src; P.ld_src = ld_src; P.gsc = gsc; P.gsh = gsh;
   P.n = n; P.m = m; P.Lf = Lf;
-  P.status = status;
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);
@@ -397,9 +397,9 @@ static int gemm_gen_launch_t(const GemmP& g, const uint4* Wp, float out_scale, c
 
 template <int GEN>
 static int gemm_gen_launch(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
-                           const float* gsc, const float* gsh, int n, int m, int Lf, int* status, cudaStream_t st) {
+                           const float* gsc, const float* gsh, int n, int m, int Lf, cudaStream_t st) {
   // debug bit 10 (1024): producers without the software pipeline (A/B runs)
   const bool pipe = !(mm_debug_flags() & 1024) && (GEN == gen::GEN_NORM ? (mm_debug_flags() & 4096) != 0 : m == 128);
-  if (pipe) return gemm_gen_launch_t<GEN, true>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, status, st);
-  return gemm_gen_launch_t<GEN, false>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, status, st);
+  if (pipe) return gemm_gen_launch_t<GEN, true>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, st);
+  return gemm_gen_launch_t<GEN, false>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, st);
 }

@@ -41,7 +41,10 @@ struct TmaP {
   long plane_elems;         // output: distance (in fp16 elements) between the hi and lo planes
   int ksegs, kc_per_seg;    // conv: K is accumulated in `ksegs` TMEM passes of kc_per_seg chunks whose fp32
   float* acc_scratch;       // partial sums are combined in fp32 RN through acc_scratch[pixel][M] (see launcher)
-  int halo, pool;           // pixel-major kernel only (gemm_tma_px.cuh): vertical taps from one halo box; fused 2x2 max-pool
+  int halo, pool;           // halo: pixel-major kernel only (gemm_tma_px.cuh), vertical taps from one halo box
+                            // pool: fused 2x2 max-pool in the conv epilogue (both kernels): the pooled map is written
+  unsigned long long* pool_sum;   // channel-major conv + pool: if set, the pooled values are also summed per (image, channel)
+                            // into pool_sum[img][M] as 2^-32 fixed point (SkipPool's global average, order-independent)
   unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
   int* status;              // workspace status word (FP16 range flag of the planar outputs) or null
@@ -86,6 +89,19 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
       : "f"(x));
   hi = __ushort_as_half(a);
   lo = __ushort_as_half(b);
+}
+
+// 2x2 max-pool of one 32-column chunk held by a thread (one channel): the chunk is 32/BX box rows of BX pixels, so its
+// 16/BX row pairs hold BX/2 windows each: o[a*(BX/2) + b] = window (rows 2a, 2a+1; columns 2b, 2b+1).  BX <= 16.
+template <int BX>
+__device__ __forceinline__ void pool_chunk(const float (&x)[32], float (&o)[8]) {
+#pragma unroll
+  for (int a = 0; a < 16 / BX; a++)
+#pragma unroll
+    for (int b = 0; b < BX / 2; b++) {
+      const int i = 2 * a * BX + 2 * b;
+      o[a * (BX / 2) + b] = fmaxf(fmaxf(x[i], x[i + 1]), fmaxf(x[i + BX], x[i + BX + 1]));
+    }
 }
 
 static __global__ void __launch_bounds__(T_THREADS, 1)
@@ -187,6 +203,70 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
       const int img = i0 + ii, y = y0 + yy, xg = x0 + xx;
       store_rows(x, img < P.n_img && y < P.H && xg < P.W, (((long)img * P.H + y) * P.W + xg) * p.y_ms + cb);
     };
+    // ---- fused 2x2 max-pool (P.pool): the thread owns one channel of the tile's columns, so every pooling window of
+    // its chunks is in its own registers.  NP pooled pixels per emission (8 for bx <= 16; 16 for bx == 32, where a
+    // chunk is one box row and the previous chunk's horizontal maxima are kept); lane q < NP stores pooled pixel q's
+    // 32 channels.  The pooled values are also summed per (image, channel) for SkipPool's global average.
+    const int Hp = P.H >> 1, Wp = P.W >> 1;
+    float hprev[16];            // bx == 32: horizontal maxima of the even row
+    float psum = 0.f;           // running sum of this thread's pooled values of image psum_img
+    int psum_img = -1;
+    auto pool_flush = [&](int co_) {
+      if (P.pool_sum && psum_img >= 0 && psum_img < P.n_img)
+        atomicAdd(P.pool_sum + (long)psum_img * p.M + co_, __float2ull_rn(psum * 4294967296.f));
+      psum = 0.f; psum_img = -1;
+    };
+    // o[q], q < NP: pooled pixels of box rows (r0, r0 + 1), columns 2q', in box-row units r = ii*by + yy
+    auto pool_emit = [&](const float (&o)[16], int np, int r0, int rstep_q, int wq, int cb, int co_, int i0, int y0, int x0) {
+      // pooled pixel q: box row r0 + 2*(q / wq), box column 2*(q % wq)      (wq = windows per row pair)
+      float xs[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) xs[j] = j < 16 ? o[j] : 0.f;
+      const int q = lane < np ? lane : 0;
+      const int r = r0 + 2 * (q / wq), xx = 2 * (q - (q / wq) * wq);
+      const int yy = r & (P.by - 1), ii = r >> lby;
+      const int img = i0 + ii, y = y0 + yy, xg = x0 + xx;
+      const bool ok = lane < np && img < P.n_img && y < P.H && xg < P.W;
+      store_rows(xs, ok, (((long)img * Hp + (y >> 1)) * Wp + (xg >> 1)) * p.y_ms + cb);
+      if (P.pool_sum) {
+        (void)rstep_q;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          if (j < np) {
+            const int rj = r0 + 2 * (j / wq), xj = 2 * (j - (j / wq) * wq);
+            const int imj = i0 + (rj >> lby);
+            const bool okj = imj < P.n_img && y0 + (rj & (P.by - 1)) < P.H && x0 + xj < P.W;
+            if (imj != psum_img) { pool_flush(co_); psum_img = imj; }
+            if (okj) psum += o[j];
+          }
+        }
+      }
+    };
+    // one finished 32-column chunk (bias + ReLU applied) of channel co_: store it, or pool it and store the pooled map
+    auto emit_conv = [&](const float (&x)[32], int cc, int col0, int co_, int i0, int y0, int x0) {
+      if (!P.pool) { store_planar_block(x, col0, co_ - lane, i0, y0, x0); return; }
+      float o[16];
+      const int r0 = col0 >> lbx;
+      if (P.bx == 32) {
+        if (!(cc & 1)) {
+#pragma unroll
+          for (int b = 0; b < 16; b++) hprev[b] = fmaxf(x[2 * b], x[2 * b + 1]);
+          return;
+        }
+#pragma unroll
+        for (int b = 0; b < 16; b++) o[b] = fmaxf(hprev[b], fmaxf(x[2 * b], x[2 * b + 1]));
+        pool_emit(o, 16, r0 - 1, 0, 16, co_ - lane, co_, i0, y0, x0);
+        return;
+      }
+      float o8[8];
+      if (P.bx == 16) pool_chunk<16>(x, o8);
+      else if (P.bx == 8) pool_chunk<8>(x, o8);
+      else if (P.bx == 4) pool_chunk<4>(x, o8);
+      else pool_chunk<2>(x, o8);
+#pragma unroll
+      for (int j = 0; j < 16; j++) o[j] = j < 8 ? o8[j] : 0.f;
+      pool_emit(o, 8, r0, 0, P.bx >> 1, co_ - lane, co_, i0, y0, x0);
+    };
 
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mg = (int)(t % mgroups);
@@ -235,9 +315,10 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
                 float a = fmaf(__uint_as_float(v[j]), P.t.out_scale, sv[j]) + bv;
                 sv[j] = p.relu ? fmaxf(a, 0.f) : a;
               }
-              store_planar_block(sv, col0, co - lane, i0, y0, x0);
+              emit_conv(sv, cc, col0, co, i0, y0, x0);
             }
           }
+          if (P.pool && seg == P.ksegs - 1 && rowok) pool_flush(co);
         }
       } else
       for (int mt = 0; mt < MT; mt++) {
@@ -350,7 +431,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
             float xv[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) xv[j] = __uint_as_float(v[j]);
-            store_planar_block(xv, col0, co - lane, i0, y0, x0);
+            emit_conv(xv, cc, col0, co, i0, y0, x0);
           } else {
             const int nvalid = min(32, len - col0);
             const long row0 = (long)g * p.y_gs + c0 + col0;
@@ -384,6 +465,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
           }
         }
         if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2(d1, d2);
+        if (P.conv && P.pool && rowok) pool_flush(co);
       }
       tc_fence_before();
       __syncwarp();
@@ -578,7 +660,7 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
 static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                 int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st,
                                 float* acc_scratch = nullptr, long y_plane_pooled = 0, int* did_pool = nullptr,
-                                int* status = nullptr) {
+                                int* status = nullptr, unsigned long long* pool_sum = nullptr) {
   if (did_pool) *did_pool = 0;
   if (!Wp || C % tc::BK) return MMMOT_E_ARG;
   int sms = 0;
@@ -617,6 +699,13 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
       P.pool = 1;
       *did_pool = 1;
     }
+  }
+  // channel-major kernel: the 2x2 max-pool (and SkipPool's per-image sums) fused into the epilogue when every pooling
+  // window lies inside one thread's chunks: box rows of <= 32 pixels, an even number of box rows per 128-column half
+  if (!px && y_plane_pooled > 0 && did_pool && bx >= 2 && bx <= 32 && by >= 2 && !(H & 1) && !(W & 1) && !(dbg & 512)) {
+    P.pool = 1;
+    P.pool_sum = pool_sum;
+    *did_pool = 1;
   }
   P.tiles_x = mm_cdiv(W, bx); P.tiles_y = mm_cdiv(H, by);
   P.n_img = n_img; P.H = H; P.W = W; P.C = C;

@@ -52,7 +52,7 @@ static inline int stats_reduce(const double2* part, int M, int G, int tpg, const
 static __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const int* __restrict__ cnt,
                                    int uniform, int G, int C, int cpg, int stats_ld, int c_off,
-                                   float* __restrict__ sc, float* __restrict__ sh) {
+                                   float* __restrict__ sc, float* __restrict__ sh, int* status) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= G * C) return;
   int g = idx / C, c = idx - g * C;
@@ -70,13 +70,17 @@ static __global__ void gn_finalize_kernel(const double* __restrict__ stats, cons
   double a = (double)gamma[c] * rstd;
   sc[idx] = (float)a;
   sh[idx] = (float)((double)beta[c] - mean * a);
+  // FP16 range guard for consumers that convert relu(x*sc + sh) to FP16 hi/lo without looking at it (gemm_gen.cuh):
+  // a value of a group of n elements lies within sqrt(n) standard deviations of the group mean, so
+  // |GN(x)| <= sqrt(n)*|gamma| + |beta|.  (Never triggers for sane checkpoints: needs |gamma| > ~250 at n = 65536.)
+  if (status && sqrt(n) * fabs((double)gamma[c]) + fabs((double)beta[c]) >= 65504.0) atomicOr(status, 1);
 }
 
 static inline int gn_finalize(const double* stats, const float* gamma, const float* beta, const int* cnt,
                               int uniform, int G, int C, int cpg, float* sc, float* sh,
-                              cudaStream_t st, int stats_ld = 0, int c_off = 0) {
+                              cudaStream_t st, int stats_ld = 0, int c_off = 0, int* status = nullptr) {
   gn_finalize_kernel<<<mm_cdiv((long)G * C, 256), 256, 0, st>>>(
-      stats, gamma, beta, cnt, uniform, G, C, cpg, stats_ld ? stats_ld : C, c_off, sc, sh);
+      stats, gamma, beta, cnt, uniform, G, C, cpg, stats_ld ? stats_ld : C, c_off, sc, sh, status);
   MM_LAUNCH_CHECK();
   return 0;
 }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "norm_ops.cuh"
+#include "gemm_gen.cuh"
 #include "tc_ops.cuh"
 
 namespace {
@@ -224,6 +225,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     // layer i writes fp32 Y[p][cout] + GroupNorm partials; norm_split turns it into the packed FP16
     // operand of layer i+1.  y1's packed form (x1p) is kept for the head.
     float* ybuf[5] = {w.y1, w.t0, w.t1, w.t0, nullptr};
+    const bool gen_mid = !(mm_debug_flags() & 8192);   // debug bit 13: layers 3, 4 through norm_split + the TMA-fed kernel
     for (int i = 0; i < 5; i++) {
       const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
       GemmP p = gemm_defaults();
@@ -239,20 +241,28 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
         pn_l1_stats_kernel<<<(int)tiles.size(), 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
         MM_LAUNCH_CHECK();
         if (timed) mm_timing_end(st);
-      } else {                                                  // FP16 hi/lo planes [2][P][cin] via TMA
-        // compulsory traffic: operand planes in (4 B per element) + fp32 activation out (none for the statistics pass)
+      } else {
+        // compulsory traffic: activation in (4 B per element) + fp32 activation out (none for the statistics pass)
         if (timed) mm_timing_begin(st, i == 4 ? MM_T_PN_L5A : MM_T_PN_L2 + (i - 1), 2.0 * cout[i] * cin[i] * cols,
                                    4.0 * (cin[i] + (i == 4 ? 0 : cout[i])) * cols);
-        MM_TRY(gemm_tma_launch_mat(p, wp, wps, i == 1 ? w.x1p : w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st));
+        if (gen_mid && (i == 2 || i == 3)) {
+          // layers 3, 4: GroupNorm + ReLU of the previous layer applied by this contraction's operand producers
+          // (gemm_gen.cuh) straight from its fp32 output: no normalised copy is written
+          MM_TRY((gemm_gen_launch<gen::GEN_NORM>(p, wp, wps, ybuf[i - 1], cin[i], w.sc, w.sh, 0, 0, 0, st)));
+        } else {                                                // FP16 hi/lo planes [2][P][cin] via TMA
+          MM_TRY(gemm_tma_launch_mat(p, wp, wps, i == 1 ? w.x1p : w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st));
+        }
         if (timed) mm_timing_end(st);
       }
       MM_TRY(stats_reduce(w.part, cout[i], pairs, 0, w.gstart, w.stats, st, 2));
-      MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st));
+      MM_TRY(gn_finalize(w.stats, q[2], q[3], w.cnt, 0, pairs, cout[i], 1, w.sc, w.sh, st, 0, 0, ar.status()));
       if (i == 0) {
         if (timed) mm_timing_begin(st, MM_T_PN_L1, 0.0, (12.0 + 4.0 * 64) * cols);
         pn_l1_apply_kernel<<<mm_cdiv(P * 16, 256), 256, 0, st>>>(points, q[0], q[1], w.sc, w.sh, w.seg, L, P, w.x1p, ar.status());
         MM_LAUNCH_CHECK();
         if (timed) mm_timing_end(st);
+      } else if (gen_mid && (i == 1 || i == 2)) {
+        // consumed in place by the next layer's producers
       } else if (i < 4) {
         if (timed) mm_timing_begin(st, MM_T_PN_NORM, 0.0, 8.0 * cout[i] * cols);
         MM_TRY(norm_split(ybuf[i], cout[i], w.sc, w.sh, cout[i], P, 0, w.seg, L, w.xp, st, ar.status()));

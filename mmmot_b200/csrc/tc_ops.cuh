@@ -66,3 +66,13 @@ static inline int transpose_f32(const float* src, float* dst, int rows, int cols
   MM_LAUNCH_CHECK();
   return 0;
 }
+
+// Range guard of the pairwise producers (gemm_gen.cuh GEN_PAIR_*), which convert f_i (*|-) f_j to FP16 hi/lo unseen:
+// flag the status word when a feature is large enough for the op to reach 65504 (|f| >= 255.9 for the product,
+// |f| >= 65504 for the differences).  feats [n] fp32.
+static __global__ void feats_range_kernel(const float* __restrict__ f, long n, float limit, int* status) {
+  float amax = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    amax = fmaxf(amax, fabsf(f[i]));
+  if (status && !(amax < limit)) atomicOr(status, 1);
+}

@@ -29,8 +29,11 @@ WORST_EL = 4.0
 
 
 def frac_outside(a, b, rtol=RTOL_EL, atol=ATOL_EL):
-    """Fraction of elements violating |a-b| <= rtol*|ref| + atol, and the worst ratio |a-b| / (rtol*|ref| + atol)."""
+    """Fraction of elements violating |a-b| <= rtol*|ref| + atol', and the worst ratio |a-b| / (rtol*|ref| + atol').
+    atol' = max(atol, 1e-5 * max|ref|): for tensors whose scale is far above 1 (raw link logits of softmax_mode 'none')
+    the absolute floor follows the tensor's scale, at a tenth of the max-norm bound."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    atol = max(atol, 1e-5 * float(b.abs().max()))
     bound = rtol * b.abs() + atol
     ratio = (a - b).abs() / bound
     return float((ratio > 1).double().mean()), float(ratio.max())
