@@ -9,6 +9,8 @@
 // the MLP layers is applied by the next contraction's producers while they build its operand, so
 // each layer output crosses HBM once as channels-last fp32 (written by one epilogue, read by the
 // next layer's producers).
+#include <algorithm>
+
 #include "norm_ops.cuh"
 #include "gemm_gen.cuh"
 #include "tc_ops.cuh"
@@ -82,33 +84,44 @@ __global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __rest
     V[(long)c * ldv + (long)g * (M + N) + (is_end ? M + r : r - N)] = acc / (float)cnt;
   }
 }
-// z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : 8 lanes per row (4 float4 each), fixed-order shuffle tree
-__global__ void link_logit_cl_kernel(const float* __restrict__ y3, const float* __restrict__ sc,
-                                     const float* __restrict__ sh, const float* __restrict__ w4,
-                                     const float* __restrict__ b4, long rows, int NM, float* __restrict__ z) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long row = t >> 3;
-  const int sub = (int)(t & 7);
-  float acc = 0.f;
-  if (row < rows) {
-    const int g = (int)(row / NM);
+// z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : one warp per row (a lane owns 4 channels: one coalesced 512-byte
+// load per row, its GroupNorm affine and w4 in registers while the group stays the same), fixed-order shuffle tree
+__global__ void __launch_bounds__(256) link_logit_cl_kernel(const float* __restrict__ y3, const float* __restrict__ sc,
+                                                            const float* __restrict__ sh, const float* __restrict__ w4,
+                                                            const float* __restrict__ b4, long rows, int NM,
+                                                            float* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const float4 w = *reinterpret_cast<const float4*>(w4 + lane * 4);
+  const float bias = b4[0];
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  int gcur = -1;
+  // each warp takes a contiguous block of rows (the group changes at most a few times per warp)
+  const long per = (rows + nwarps - 1) / nwarps;
+  const long r0 = warp * per, r1 = min(rows, r0 + per);
+  for (long row = r0; row < r1; row += 4) {
+    float4 x[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int c = (sub * 4 + q) * 4;
-      const float4 x = *reinterpret_cast<const float4*>(y3 + row * 128 + c);
-      const float4 a = *reinterpret_cast<const float4*>(sc + g * 128 + c);
-      const float4 b = *reinterpret_cast<const float4*>(sh + g * 128 + c);
-      const float4 w = *reinterpret_cast<const float4*>(w4 + c);
-      acc = fmaf(w.x, fmaxf(fmaf(x.x, a.x, b.x), 0.f), acc);
-      acc = fmaf(w.y, fmaxf(fmaf(x.y, a.y, b.y), 0.f), acc);
-      acc = fmaf(w.z, fmaxf(fmaf(x.z, a.z, b.z), 0.f), acc);
-      acc = fmaf(w.w, fmaxf(fmaf(x.w, a.w, b.w), 0.f), acc);
+    for (int u = 0; u < 4; u++)
+      if (row + u < r1) x[u] = __ldcs(reinterpret_cast<const float4*>(y3 + (row + u) * 128 + lane * 4));
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (row + u >= r1) break;
+      const int g = (int)((row + u) / NM);
+      if (g != gcur) {
+        gcur = g;
+        a = *reinterpret_cast<const float4*>(sc + g * 128 + lane * 4);
+        b = *reinterpret_cast<const float4*>(sh + g * 128 + lane * 4);
+      }
+      float acc = w.x * fmaxf(fmaf(x[u].x, a.x, b.x), 0.f);
+      acc = fmaf(w.y, fmaxf(fmaf(x[u].y, a.y, b.y), 0.f), acc);
+      acc = fmaf(w.z, fmaxf(fmaf(x[u].z, a.z, b.z), 0.f), acc);
+      acc = fmaf(w.w, fmaxf(fmaf(x[u].w, a.w, b.w), 0.f), acc);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) z[row + u] = acc + bias;
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (row < rows && sub == 0) z[row] = acc + b4[0];
 }
 
 // Tile table for the new/end MLP: group 2g = new columns (len M), 2g+1 = end columns (len N).
@@ -389,8 +402,9 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   float* zdst = softmax_mode == MMMOT_SM_NONE ? link : w.z;
   if (use_tc) {
     if (timed) mm_timing_begin(st, MM_T_AFF_LOGIT, 2.0 * 128 * (double)G * NM, 4.0 * 129 * (double)G * NM);
-    link_logit_cl_kernel<<<mm_cdiv((long)G * NM * 8, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
-                                                                        W[MMMOT_W_AF_B4], (long)G * NM, NM, zdst);
+    const long lrows = (long)G * NM;
+    link_logit_cl_kernel<<<(int)std::min<long>(148L * 8, (lrows + 31) / 32), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
+                                                                                      W[MMMOT_W_AF_B4], lrows, NM, zdst);
   } else {
     link_logit_kernel<<<mm_cdiv((long)G * NM, 256), 256, 0, st>>>(w.y3, w.sc3, w.sh3, W[MMMOT_W_AF_W4],
                                                                  W[MMMOT_W_AF_B4], G, NM, zdst);
