@@ -363,7 +363,18 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is created: keep stdout for the one
+        # JSON line (the banner goes to stderr)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
     mmmot_b200.set_engine(args.engine)
     if args.kseg >= 0:
