@@ -94,7 +94,14 @@ enum mmmot_weight_id {
   MMMOT_W_PN_WP1 = 152,           /* .. +4 : PointNet trunk layers 1..5 */
   MMMOT_W_PN_WHAP = 157,
   MMMOT_W_AF_W01P = 158, MMMOT_W_AF_W2P = 159, MMMOT_W_AF_W3P = 160,
-  MMMOT_W_COUNT = 161
+  /* ---- training-mode operands: the UNFOLDED conv weights / biases and the BatchNorm affines of the
+     layers whose BatchNorm uses batch statistics in .train() */
+  MMMOT_W_VGG_RAWW0 = 161,        /* .. +12 : Wt[(ky*3+kx)*Cin + ci][Cout], not folded */
+  MMMOT_W_VGG_RAWB0 = 174,        /* .. +12 */
+  MMMOT_W_VGG_BNW0 = 187,         /* .. +12 : BatchNorm2d weight */
+  MMMOT_W_VGG_BNB0 = 200,         /* .. +12 : BatchNorm2d bias */
+  MMMOT_W_WD_RAW0 = 213,          /* .. +7  : w_det w1t b1 bn1_w bn1_b w2t b2 bn2_w bn2_b */
+  MMMOT_W_COUNT = 221
 };
 
 typedef struct mmmot_weights {
@@ -152,6 +159,24 @@ size_t mmmot_fusion_det_workspace(int pairs, int L);
 int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, int score_flags, float neg_threshold,
                          int pairs, int L, float* feats, float* det_scores,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training-mode variants of the two stages that contain BatchNorm: in .train() the reference's
+ * BatchNorm2d layers of the VGG trunk (modules/vgg.py:67-80) and BatchNorm1d layers of w_det (modules/tracking_net.py:
+ * 92-100) use the statistics of the current batch, and det_scores stay raw logits (tracking_net.py:152-162).  FP32 FFMA
+ * engine; one frame-pair = one batch (the reference trains on one sample per step, tracking_model.py:50-66).
+ *   mmmot_appearance_train_fwd: as mmmot_appearance_fwd; bn_stats [13][2][512] = per layer (batch mean | biased batch
+ *     variance) per channel, for the caller's running-average update.
+ *   mmmot_w_det_train_fwd: feats [3][512][L] of one pair -> det_scores [3][L] raw logits; bn_stats [2][2][512].
+ * The other stages (PointNet, fusion, affinity) have no BatchNorm: the eval entry points serve both modes
+ * (mmmot_fusion_det_fwd's det_scores are simply overwritten by mmmot_w_det_train_fwd's).  Forward only: no gradients.
+ */
+size_t mmmot_appearance_train_workspace(int n_img, int H, int W);
+int mmmot_appearance_train_fwd(const mmmot_weights* wts, const float* crops, int n_img, int H, int W, int L,
+                               float* feats, float* bn_stats, void* workspace, size_t workspace_bytes, void* stream);
+size_t mmmot_w_det_train_workspace(int L);
+int mmmot_w_det_train_fwd(const mmmot_weights* wts, int L, const float* feats, float* det_scores, float* bn_stats,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pairwise affinity + start/end indicator + softmax mode.

@@ -29,7 +29,8 @@ W = dict(
     AF_W4=127, AF_B4=128,
     NE_W1T=129, NE_B1=130, NE_G1W=131, NE_G1B=132, NE_W2T=133, NE_B2=134, NE_G2W=135, NE_G2B=136,
     NE_W3=137, NE_B3=138,
-    VGG_WP0=139, PN_WP1=152, PN_WHAP=157, AF_W01P=158, AF_W2P=159, AF_W3P=160, COUNT=161,
+    VGG_WP0=139, PN_WP1=152, PN_WHAP=157, AF_W01P=158, AF_W2P=159, AF_W3P=160,
+    VGG_RAWW0=161, VGG_RAWB0=174, VGG_BNW0=187, VGG_BNB0=200, WD_RAW0=213, COUNT=221,
 )
 
 
@@ -65,6 +66,10 @@ SIGNATURES = {
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),
     "mmmot_appearance_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "mmmot_appearance_train_workspace": (_sz, [_i, _i, _i]),
+    "mmmot_appearance_train_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_w_det_train_workspace": (_sz, [_i]),
+    "mmmot_w_det_train_fwd": (_i, [_wp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_pointnet_workspace": (_sz, [_i, _i, _l]),
     "mmmot_pointnet_fwd": (_i, [_wp, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "mmmot_fusion_det_workspace": (_sz, [_i, _i]),

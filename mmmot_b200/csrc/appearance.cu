@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(128) skip_head_kernel(
 
 }  // namespace
 
+int mm_launch_skip_heads(const mmmot_weights* wts, float* const* pooled, int n_img, int L, float* feats, cudaStream_t st);
+
 extern "C" size_t mmmot_appearance_workspace(int n_img, int H, int W) {
   MmArena a(nullptr, 0);
   size_t act = (size_t)n_img * 64 * H * W;
@@ -411,6 +413,11 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
     }
   }
   }
+  return mm_launch_skip_heads(wts, pooled, n_img, L, feats, st);
+}
+
+// the four SkipPool heads on the pooled maps -> stack 0 of feats (shared with the training-mode variant, train.cu)
+int mm_launch_skip_heads(const mmmot_weights* wts, float* const* pooled, int n_img, int L, float* feats, cudaStream_t st) {
   for (int s = 0; s < 4; s++) {
     const float* const* q = &wts->w[MMMOT_W_SKIP0 + 10 * s];
     int C = kSkipC[s], mid = C / 4 > 64 ? C / 4 : 64;

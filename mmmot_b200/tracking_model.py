@@ -28,7 +28,9 @@ def _flags(x):
 
 
 class TrackingModule(object):
-    """Evaluation-side twin of the reference class (training ``step`` is out of scope)."""
+    """Twin of the reference class: the evaluation side (predict / id stitching) and the forward half of the training
+    ``step`` (training-mode forward, ground-truth generation, loss value).  The CUDA library is forward
+    only, so ``step`` returns the loss without calling backward / the optimizer."""
 
     def __init__(self, model, optimizer=None, criterion=None, det_type="3D"):
         self.model = model
@@ -51,7 +53,48 @@ class TrackingModule(object):
         self.clear_mem()
 
     def train(self):
-        raise NotImplementedError("mmmot_b200 implements the evaluation path only (SURVEY §8f N4)")
+        for m in (self.model if isinstance(self.model, list) else [self.model]):
+            m.train()
+        self.clear_mem()
+
+    # ------------------------------------------------------------------ training step (forward half)
+    def step(self, det_img, det_info, det_id, det_cls, det_split):
+        """tracking_model.py:50-66 up to the loss: training-mode forward -> generate_gt -> criterion.  The reference then
+        calls loss.backward() and optimizer.step(); the CUDA library builds no autograd graph, so the loss VALUE is
+        returned (a detached tensor) and the parameters are left untouched."""
+        det_score, link_score, new_score, end_score, trans = self.model(det_img, det_info, det_split)
+        gt_det, gt_link, gt_new, gt_end = self.generate_gt(det_score[0], det_cls, det_id, det_split)
+        return self.criterion(det_split, gt_det, gt_link, gt_new, gt_end, det_score, link_score, new_score, end_score, trans)
+
+    def generate_gt(self, det_score, det_cls, det_id, det_split):
+        """tracking_model.py:294-351 without the per-detection Python loops: a detection is a positive when its class
+        flag is 1; positives of consecutive frames with the same track id are linked (first match wins, as the
+        reference's ``break``); a positive without successor ends, one without predecessor is new.  det_cls / det_id:
+        per frame, tensors of shape 1 x n_i (the DataLoader layout)."""
+        split = [int(s) for s in det_split]
+        L = sum(split)
+        dev, dt = det_score.device, det_score.dtype
+        cls = [torch.as_tensor(c).reshape(-1).to(dev) == 1 for c in det_cls]
+        ids = [torch.as_tensor(i).reshape(-1).to(dev) for i in det_id]
+        gt_det = torch.cat(cls).to(dt)
+        gt_new, gt_end, gt_link = torch.zeros(L, device=dev, dtype=dt), torch.zeros(L, device=dev, dtype=dt), []
+        start = 0
+        for i, n in enumerate(split):
+            pos = cls[i]
+            has_succ = torch.zeros(n, dtype=torch.bool, device=dev)
+            if i + 1 < len(split):
+                same = ids[i][:, None] == ids[i + 1][None, :]                    # any class on the next frame
+                first = same & (same.cumsum(1) == 1)                             # the first match only
+                link = (first & pos[:, None]).to(dt)
+                gt_link.append(link.unsqueeze(0))
+                has_succ = link.sum(1) > 0
+            has_pred = torch.zeros(n, dtype=torch.bool, device=dev)
+            if i > 0:
+                has_pred = (ids[i][:, None] == ids[i - 1][None, :]).any(1)
+            gt_end[start:start + n] = (pos & ~has_succ).to(dt)
+            gt_new[start:start + n] = (pos & ~has_pred).to(dt)
+            start += n
+        return gt_det, gt_link, gt_new, gt_end
 
     # ------------------------------------------------------------------ predict
     @torch.no_grad()

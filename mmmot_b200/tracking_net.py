@@ -18,7 +18,10 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .schema import BUFFER_KINDS, state_schema
+from .schema import BUFFER_KINDS, VGG_POOL_AFTER, VGG_STAGES, state_schema
+
+# conv k of the 13 is followed by a 2x2 max-pool (so the map of conv k+1 is 4x smaller)
+VGG_POOLED_BEFORE = [idx in VGG_POOL_AFTER[s] for s, stage in enumerate(VGG_STAGES) for idx, _, _ in stage]
 from .weights import DeviceWeights
 
 
@@ -278,12 +281,90 @@ class TrackingNet(nn.Module):
         out.update(solve_batch(out["det"][:, t], out["link"][:, t], new_p[:, t], end_p[:, t], n, m))
         return out
 
+    # ------------------------------------------------------------------ training-mode forward
+    # (name in state_dict of the BatchNorm, number of channels) in the order of the bn_stats rows the library returns
+    _VGG_BN = [f"appearance.layers.{s}.{idx + 1}" for s, stage in enumerate(VGG_STAGES) for idx, _, _ in stage]
+
+    def _update_running(self, prefix, mean, var_biased, count, momentum=0.1):
+        """torch.nn.BatchNorm semantics in .train(): running = (1 - m) * running + m * batch, with the UNBIASED batch
+        variance; num_batches_tracked += 1."""
+        mod = self
+        for part in prefix.split("."):
+            mod = mod._modules[part]
+        unbiased = var_biased * (count / max(count - 1.0, 1.0))
+        mod.running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+        mod.running_var.mul_(1 - momentum).add_(unbiased, alpha=momentum)
+        mod.num_batches_tracked += 1
+
+    @torch.no_grad()
+    def _forward_train(self, dets, det_info, dets_split):
+        """reference TrackingNet.forward with self.training (modules/tracking_net.py:152-162, 183-192): BatchNorm layers
+        (VGG trunk, w_det) normalise with the statistics of this sample and update their running averages, det_scores are
+        raw logits without the neg_threshold step, new/end scores are not zero-padded.  Forward only — no autograd graph
+        is built through the CUDA library.  DropBlock / Dropout are not implemented (the four pp_* configs switch them
+        off: dropblock 0, use_dropout False)."""
+        if self.dropblock or self.use_dropout:
+            raise NotImplementedError("mmmot_b200.TrackingNet training-mode forward: dropblock / use_dropout are not implemented")
+        if len(dets_split) != 2:
+            raise NotImplementedError("mmmot_b200.TrackingNet supports 2-frame samples (sample_max_len: 2)")
+        n, m = int(dets_split[0]), int(dets_split[1])
+        L = n + m
+        lib = _lib.load()
+        self._prepared = None                      # parameters move under an optimizer: re-derive the operands every step
+        wts = self.prepared()
+        dev = wts.flat.device
+        crops = dets.contiguous().float()
+        points = det_info['points'].reshape(-1, det_info['points'].shape[-1])[:, :3].contiguous().float()
+        split = det_info['points_split'].reshape(-1).detach().to("cpu", torch.int32).contiguous()
+        if crops.device != dev or points.device != dev or crops.shape[0] != L or split.numel() != L + 1:
+            raise _lib.MmmotError("inputs do not match the module's device / dets_split")
+        H, W = crops.shape[-2:]
+        feats = torch.empty(1, 3, 512, L, device=dev)
+        det = torch.empty(1, 3, L, device=dev)
+        link = torch.empty(1, 3, n, m, device=dev)
+        new = torch.empty(1, 3, m, device=dev)
+        end = torch.empty(1, 3, n, device=dev)
+        bn_vgg = torch.zeros(13, 2, 512, device=dev)
+        bn_det = torch.zeros(2, 2, 512, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            need = max(lib.mmmot_appearance_train_workspace(L, H, W), lib.mmmot_pointnet_workspace(1, L, int(split[-1])),
+                       lib.mmmot_fusion_det_workspace(1, L), lib.mmmot_affinity_workspace(1, n, m),
+                       lib.mmmot_w_det_train_workspace(L))
+            ws = self._workspace(need, dev)
+            wsp, wsn = vp(ws), ctypes.c_size_t(ws.numel())
+            _lib.check(lib.mmmot_status_reset(wsp, st), "mmmot_status_reset")
+            _lib.check(lib.mmmot_appearance_train_fwd(wts.ptr, vp(crops), L, H, W, L, vp(feats), vp(bn_vgg), wsp, wsn, st),
+                       "mmmot_appearance_train_fwd")
+            hs = split.numpy()
+            _lib.check(lib.mmmot_pointnet_fwd(wts.ptr, vp(points), vp(split.to(dev)), ctypes.c_void_p(hs.ctypes.data), 1, L,
+                                              vp(feats), wsp, wsn, st), "mmmot_pointnet_fwd")
+            _lib.check(lib.mmmot_fusion_det_fwd(wts.ptr, _lib.FUSION[self.score_fusion_arch], 0, 0.0, 1, L, vp(feats), vp(det),
+                                                wsp, wsn, st), "mmmot_fusion_det_fwd")
+            _lib.check(lib.mmmot_w_det_train_fwd(wts.ptr, L, vp(feats), vp(det), vp(bn_det), wsp, wsn, st), "mmmot_w_det_train_fwd")
+            _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op], _lib.SOFTMAX.get(self.softmax_mode, 0),
+                                              1, n, m, vp(feats), vp(link), vp(new), vp(end), wsp, wsn, st), "mmmot_affinity_fwd")
+            _lib.check(lib.mmmot_status_check(wsp, st), "mmmot_b200.TrackingNet training forward")
+        # running averages (reference: nn.BatchNorm2d / BatchNorm1d side effect of a training-mode forward)
+        h, w_ = H, W
+        for i, cout in enumerate(cout for stage in VGG_STAGES for _, _, cout in stage):
+            self._update_running(self._VGG_BN[i], bn_vgg[i, 0, :cout], bn_vgg[i, 1, :cout], float(L * h * w_))
+            if VGG_POOLED_BEFORE[i]:
+                h, w_ = h // 2, w_ // 2
+        self._update_running("w_det.1", bn_det[0, 0, :512], bn_det[0, 1, :512], 3.0 * L)
+        self._update_running("w_det.4", bn_det[1, 0, :256], bn_det[1, 1, :256], 3.0 * L)
+        return det[0], [link[0]], new[0], end[0], [wts.trans1.unsqueeze(0).clone(), wts.trans2.unsqueeze(0).clone()]
+
     def forward(self, dets, det_info, dets_split):
         """Reference signature (modules/tracking_net.py:165): one frame-pair.
 
         dets L x 3 x H x W; det_info['points'] 1 x P x 3; det_info['points_split'] 1 x (L+1) float;
         dets_split list of two shape-(1,) int tensors.  Returns
-        (det_scores 3xL, [link_scores 3xNxM], new_scores 3xL, end_scores 3xL, trans)."""
+        (det_scores 3xL, [link_scores 3xNxM], new_scores 3xL, end_scores 3xL, trans).  In training mode the reference's
+        training branch is returned instead (see _forward_train)."""
+        if self.training:
+            return self._forward_train(dets, det_info, dets_split)
         if len(dets_split) != 2:
             raise NotImplementedError("mmmot_b200.TrackingNet supports 2-frame samples (sample_max_len: 2), "
                                       "the only case the reference's configs run (SURVEY F9)")

@@ -154,6 +154,23 @@ def prepare(state_dict, fusion):
     out[W["NE_G2W"]] = f64(f"{ne}.4.weight"); out[W["NE_G2B"]] = f64(f"{ne}.4.bias")
     out[W["NE_W3"]] = f64(f"{ne}.6.weight").reshape(-1); out[W["NE_B3"]] = f64(f"{ne}.6.bias")
 
+    # training-mode operands: unfolded conv weights + BatchNorm affines of the layers whose BatchNorm
+    # uses batch statistics in .train() (VGG trunk, w_det)
+    i = 0
+    for s_, stage in enumerate(VGG_STAGES):
+        for idx, cin, cout in stage:
+            cp, bp = f"appearance.layers.{s_}.{idx}", f"appearance.layers.{s_}.{idx + 1}"
+            out[W["VGG_RAWW0"] + i] = f64(f"{cp}.weight").permute(2, 3, 1, 0).reshape(9 * cin, cout)
+            out[W["VGG_RAWB0"] + i] = f64(f"{cp}.bias")
+            out[W["VGG_BNW0"] + i] = f64(f"{bp}.weight")
+            out[W["VGG_BNB0"] + i] = f64(f"{bp}.bias")
+            i += 1
+    r0 = W["WD_RAW0"]
+    out[r0 + 0] = f64("w_det.0.weight").squeeze(-1).t(); out[r0 + 1] = f64("w_det.0.bias")
+    out[r0 + 2] = f64("w_det.1.weight"); out[r0 + 3] = f64("w_det.1.bias")
+    out[r0 + 4] = f64("w_det.3.weight").squeeze(-1).t(); out[r0 + 5] = f64("w_det.3.bias")
+    out[r0 + 6] = f64("w_det.4.weight"); out[r0 + 7] = f64("w_det.4.bias")
+
     out = [None if t is None else t.contiguous().float() for t in out]
     # tensor-core operand tiles (bytes, viewed as float32 words for the flat buffer)
     scales = [0.0] * W["COUNT"]

@@ -158,8 +158,76 @@ def stitch_goldens():
     print("stitch", {k: len(v["steps"]) for k, v in gold.items()})
 
 
+# training-mode cases: (name, fusion, affinity_op, softmax_mode, N, M, pts, hw, ragged, seed)
+TRAIN_CASES = [
+    ("train_mul_A_n6x5", "A", "multiply", "none", 6, 5, 24, 32, True, 21),
+    ("train_subabs_dualadd_C_n7", "C", "minus_abs", "dual_add", 7, 7, 32, 32, False, 22),
+]
+
+
+# experiments/pp_pv_40e_dualadd_subabs_C/config.yaml:39-45 through utils/build_util.py:147-155
+LOSS_KW = dict(smooth_ratio=0, detloss_type="bce", det_ratio=1.5, trans_ratio=0.001, trans_last=True, linkloss_type="l2")
+
+
+def synthetic_gt(n, m, seed):
+    """Seeded class flags / track ids in the DataLoader layout generate_gt reads (per frame: 1 x n_i)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    cls = [(torch.rand(1, k, generator=g) < 0.75).long() for k in (n, m)]
+    ids0 = torch.randperm(n + 3, generator=g)[:n]
+    ids1 = torch.randperm(n + 3, generator=g)[:m]          # overlaps ids0 partly: links, births and deaths
+    return cls, [ids0.unsqueeze(0), ids1.unsqueeze(0)]
+
+
+def train_goldens():
+    """The UNMODIFIED reference in .train() mode (BatchNorm batch statistics, raw det logits, unpadded new/end) and its
+    TrackingLoss / generate_gt.  Shims: F._verify_batch_size; `Tensor.eq` returning uint8 while the loss
+    runs, because cost.py:122 computes `1 - gt_score.eq(...)`, which reference-era torch allowed on a byte mask and
+    modern torch rejects on bool; `solvers` stubbed (ortools absent; not used here)."""
+    import sys
+    import types
+    sys.path.insert(0, ref_loader.REF)
+    sys.modules.setdefault("pyproj", types.ModuleType("pyproj"))
+    if "solvers" not in sys.modules:
+        sys.modules["solvers"] = types.SimpleNamespace(ortools_solve=None)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import tracking_model as ref_tm
+        from cost import TrackingLoss
+    for case in TRAIN_CASES:
+        name, fusion, op, sm, n, m, pts, hw, ragged, seed = case
+        net = ref_loader.load_tracking_net(
+            seq_len=2, score_arch="branch_cls", appear_arch="vgg", appear_len=512, appear_skippool=True, appear_fpn=False,
+            point_arch="v1", point_len=512, without_reflectivity=True, softmax_mode=sm, affinity_op=op, end_arch="v2",
+            end_mode="avg", test_mode=2, score_fusion_arch=fusion, neg_threshold=0.2, dropblock=0, use_dropout=False)
+        sd = synthetic_state_dict(fusion, seed=seed)
+        net.load_state_dict(sd, strict=True)
+        net.train()
+        dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
+        with torch.no_grad():
+            det, link, new, end, trans = net(dets, info, split)
+        after = {k: v.clone() for k, v in net.state_dict().items() if "running_" in k or "num_batches" in k}
+        cls, ids = synthetic_gt(n, m, seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tm = ref_tm.TrackingModule(net, None, TrackingLoss(**LOSS_KW))
+        gt_det, gt_link, gt_new, gt_end = tm.generate_gt(det[0], cls, ids, split)
+        orig_eq = torch.Tensor.eq
+        torch.Tensor.eq = lambda a, b: orig_eq(a, b).to(torch.uint8)
+        try:
+            with torch.no_grad():
+                loss = tm.criterion(split, gt_det, gt_link, gt_new, gt_end, det, link, new, end, trans)
+        finally:
+            torch.Tensor.eq = orig_eq
+        out = {"case": case, "det": det, "link": link[0], "new": new, "end": end, "trans1": trans[0], "trans2": trans[1],
+               "running": after, "gt_det": gt_det, "gt_link": gt_link[0], "gt_new": gt_new, "gt_end": gt_end,
+               "loss": loss.detach().clone()}
+        torch.save(out, os.path.join(OUT, name + ".pt"))
+        print(name, float(loss), tuple(det.shape), tuple(new.shape), tuple(end.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    train_goldens()
     crop_goldens()
     resize_goldens()
     stitch_goldens()

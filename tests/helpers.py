@@ -52,10 +52,30 @@ def check_close(a, ref, tol, what, report=None, max_outside=0.0):
 
 
 def golden_cases():
+    """Eval-mode forward fixtures (training-mode ones are train_*.pt, see train_cases)."""
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt"))):
-        out.append(torch.load(f))
+        if not os.path.basename(f).startswith("train_"):
+            out.append(torch.load(f))
     return out
+
+
+def train_cases():
+    """Training-mode fixtures of the unmodified reference (oracle/make_goldens.py::train_goldens)."""
+    return [torch.load(f) for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "train_*.pt")))]
+
+
+def synthetic_gt(n, m, seed):
+    """Seeded class flags / track ids in the DataLoader layout generate_gt reads (same generator as the golden script)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    cls = [(torch.rand(1, k, generator=g) < 0.75).long() for k in (n, m)]
+    ids0 = torch.randperm(n + 3, generator=g)[:n]
+    ids1 = torch.randperm(n + 3, generator=g)[:m]
+    return cls, [ids0.unsqueeze(0), ids1.unsqueeze(0)]
+
+
+# loss configuration of the shipped experiments (config.yaml:39-45 via utils/build_util.py:147-155)
+LOSS_KW = dict(smooth_ratio=0, detloss_type="bce", det_ratio=1.5, trans_ratio=0.001, trans_last=True, linkloss_type="l2")
 
 
 def case_tol(case):

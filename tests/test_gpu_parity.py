@@ -347,3 +347,42 @@ def test_full_forward_at_baseline_config(name, fusion, op, sm, n, pts, hw):
     check_close(o["end"][0], rend[:, :n], TOL, f"{name} end", rep, max_outside=ELEM_OUTSIDE)
     assert det_close(o["det"][0], rdet, 0.2, TOL)
     print(name, rep)
+
+
+# ------------------------------------------------------------------ training mode
+from helpers import LOSS_KW, synthetic_gt, train_cases  # noqa: E402
+
+TRAIN = train_cases()
+
+
+@pytest.mark.parametrize("g", TRAIN, ids=[c["case"][0] for c in TRAIN])
+def test_training_mode_forward_and_loss_match_reference_golden(g):
+    """TrackingNet.train(): BatchNorm batch statistics in the VGG trunk and w_det, raw det logits, unpadded new/end
+    scores, running-average update, and TrackingModule.step's loss — against the UNMODIFIED reference in .train() mode."""
+    name, fusion, op, sm, n, m, pts, hw, ragged, seed = g["case"]
+    net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch="branch_cls", score_fusion_arch=fusion, affinity_op=op,
+                                 softmax_mode=sm, neg_threshold=0.2, test_mode=2, dropblock=0, use_dropout=False)
+    net.load_state_dict(synthetic_state_dict(fusion, seed=seed))
+    net.cuda().train()
+    dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
+    cls, ids = synthetic_gt(n, m, seed)
+    tm = mmmot_b200.TrackingModule(net, None, mmmot_b200.TrackingLoss(**LOSS_KW))
+    dinfo = {k: v.cuda() for k, v in info.items()}
+    det, link, new, end, trans = net(dets.cuda(), dinfo, split)
+    assert det.shape == (3, n + m) and new.shape == (3, m) and end.shape == (3, n)
+    assert relerr(det, g["det"]) < TOL and relerr(link[0], g["link"]) < TOL
+    assert relerr(new, g["new"]) < TOL and relerr(end, g["end"]) < TOL
+    sd_after = net.state_dict()
+    for k, v in g["running"].items():
+        if k.startswith("appearance.layers") or k.startswith("w_det"):
+            if k.endswith("num_batches_tracked"):
+                assert int(sd_after[k]) == int(v), k
+            else:
+                assert relerr(sd_after[k], v) < 1e-4, k
+    # the loss through TrackingModule.step (second training-mode forward: the outputs do not depend on running stats)
+    loss = tm.step(dets.cuda(), dinfo, ids, cls, split)
+    assert abs(float(loss) - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
+    # back to eval: the eval forward still works and pads / squashes as before
+    net.eval()
+    d2, l2, n2, e2, _ = net(dets.cuda(), dinfo, split)
+    assert n2.shape == (3, n + m) and (d2 <= 1).all()

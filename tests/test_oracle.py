@@ -1,6 +1,8 @@
 """CPU: the oracle restatement against the golden fixtures produced by the UNMODIFIED reference
 (oracle/make_goldens.py), plus known-answer tests the reference never had."""
 import numpy as np
+import types
+
 import pytest
 import torch
 
@@ -97,3 +99,39 @@ def test_milp_equals_assignment_reduction():
         C[n:, m:] = 0
         r, c = linear_sum_assignment(C, maximize=True)
         assert abs(C[r, c].sum() - obj) < 1e-9
+
+
+# ------------------------------------------------------------------ training mode
+from helpers import LOSS_KW, synthetic_gt, train_cases  # noqa: E402
+
+TRAIN = train_cases()
+
+
+@pytest.mark.parametrize("g", TRAIN, ids=[c["case"][0] for c in TRAIN])
+def test_train_oracle_matches_reference_golden(g):
+    """oracle/train_ref.py (training-mode forward, running-average update, loss) against the UNMODIFIED reference in
+    .train() mode; and the product's host-side pieces (generate_gt, TrackingLoss) against the same fixtures."""
+    import mmmot_b200
+    from oracle import train_ref
+    name, fusion, op, sm, n, m, pts, hw, ragged, seed = g["case"]
+    sd = synthetic_state_dict(fusion, seed=seed)
+    dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
+    (det, link, new, end, trans), stats = train_ref.forward_train(sd, dets, info, split, fusion, op, sm)
+    assert relerr(det, g["det"]) < 5e-5 and relerr(link[0], g["link"]) < 5e-5
+    assert relerr(new, g["new"]) < 5e-5 and relerr(end, g["end"]) < 5e-5
+    assert new.shape == (3, m) and end.shape == (3, n)                 # no zero padding in training mode
+    run = train_ref.running_after(sd, stats)
+    for k, v in run.items():
+        assert relerr(v, g["running"][k]) < 1e-5, k
+    assert all(int(v) == 1 for k, v in g["running"].items() if k.endswith("num_batches_tracked")
+               and (k.startswith("appearance.layers") or k.startswith("w_det")))
+    # ground truth + loss: oracle restatement and the product's torch modules, on the reference's own outputs
+    cls, ids = synthetic_gt(n, m, seed)
+    tm = mmmot_b200.TrackingModule(types.SimpleNamespace(test_mode=2), None, mmmot_b200.TrackingLoss(**LOSS_KW))
+    gt_det, gt_link, gt_new, gt_end = tm.generate_gt(g["det"][0], cls, ids, split)
+    assert torch.equal(gt_det, g["gt_det"]) and torch.equal(gt_link[0], g["gt_link"])
+    assert torch.equal(gt_new, g["gt_new"]) and torch.equal(gt_end, g["gt_end"])
+    args = (split, gt_det, gt_link, gt_new, gt_end, g["det"], [g["link"]], g["new"], g["end"], [g["trans1"], g["trans2"]])
+    kw = {k: LOSS_KW[k] for k in ("det_ratio", "trans_ratio", "trans_last")}
+    assert abs(float(train_ref.tracking_loss(*args, **kw)) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    assert abs(float(tm.criterion(*args)) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
