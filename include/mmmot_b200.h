@@ -46,6 +46,8 @@ enum { MMMOT_FUSION_A = 0, MMMOT_FUSION_B = 1, MMMOT_FUSION_C = 2 };
 enum { MMMOT_AFF_MULTIPLY = 0, MMMOT_AFF_MINUS_ABS = 1, MMMOT_AFF_MINUS = 2 };
 /* softmax_mode: reference modules/tracking_net.py:109-124 */
 enum { MMMOT_SM_NONE = 0, MMMOT_SM_SINGLE = 1, MMMOT_SM_DUAL = 2, MMMOT_SM_DUAL_ADD = 3, MMMOT_SM_DUAL_MAX = 4 };
+/* NewEndIndicator_v2 mode: reference modules/new_end.py:69-74 (mean / max of the normalised map over the other frame) */
+enum { MMMOT_END_AVG = 0, MMMOT_END_MAX = 1 };
 
 /*
  * Prepared weights.  Produced once per checkpoint by the host (mmmot_b200/weights.py) from the
@@ -181,7 +183,7 @@ int mmmot_w_det_train_fwd(const mmmot_weights* wts, int L, const float* feats, f
 /* ---------------------------------------------------------------------------------------------
  * Pairwise affinity + start/end indicator + softmax mode.
  * Replaces affinity_module.forward (modules/gcn.py:68-82), NewEndIndicator_v2.forward
- * (modules/new_end.py:62-82, mode 'avg') and TrackingNet.associate (tracking_net.py:106-126).
+ * (modules/new_end.py:62-82, modes 'avg' and 'max') and TrackingNet.associate (tracking_net.py:106-126).
  * The 3 x 512 x N x M pairwise tensor is generated tile by tile inside the first contraction's operand producers
  * (csrc/gemm_gen.cuh) and never stored; GroupNorm + ReLU between the MLP layers is applied by the next layer's
  * producers, so each layer output crosses HBM once as fp32.
@@ -190,7 +192,7 @@ int mmmot_w_det_train_fwd(const mmmot_weights* wts, int L, const float* feats, f
  *                                                tracking_net.py:183-189 does)
  */
 size_t mmmot_affinity_workspace(int pairs, int n, int m);
-int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode,
+int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode, int end_mode,
                        int pairs, int n, int m, const float* feats,
                        float* link, float* new_s, float* end_s,
                        void* workspace, size_t workspace_bytes, void* stream);

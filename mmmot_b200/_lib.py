@@ -16,6 +16,7 @@ SCORE_SIGMOID, SCORE_THRESHOLD = 1, 2
 FUSION = {"A": 0, "B": 1, "C": 2}
 AFFINITY = {"multiply": 0, "minus_abs": 1, "minus": 2}
 SOFTMAX = {"none": 0, "single": 1, "dual": 2, "dual_add": 3, "dual_max": 4}
+END_MODE = {"avg": 0, "max": 1}
 
 # weight ids: mirrors `enum mmmot_weight_id` (tests/test_abi.py parses the header and compares)
 W = dict(
@@ -75,7 +76,7 @@ SIGNATURES = {
     "mmmot_fusion_det_workspace": (_sz, [_i, _i]),
     "mmmot_fusion_det_fwd": (_i, [_wp, _i, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_affinity_workspace": (_sz, [_i, _i, _i]),
-    "mmmot_affinity_fwd": (_i, [_wp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_affinity_fwd": (_i, [_wp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_crop_workspace": (_sz, [_i, _i]),
     "mmmot_crop_count": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "mmmot_crop_scatter": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -20,10 +20,11 @@ namespace {
 // Row/column means of y = relu(GN_{1,512}(conv0 x)):  new_vec = mean_i y (per j), end_vec = mean_j y
 // (reference new_end.py:69-71).  One CTA per (g, c); V is channel-major over absolute columns:
 // V[c][g*(M+N) + j] (new part), V[c][g*(M+N) + M + i] (end part).
+// mx: reduce with max instead of the mean (NewEndIndicator_v2 mode 'max', new_end.py:73-74; values are >= 0 after the ReLU).
 __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restrict__ y0, long y_gs,
                                                           const float* __restrict__ sc,
                                                           const float* __restrict__ sh, int N, int M,
-                                                          long ldv, float* __restrict__ V) {
+                                                          long ldv, float* __restrict__ V, int mx) {
   extern __shared__ float colacc[];  // [warps][M]: per-warp partial column sums, combined in fixed order
   const int g = blockIdx.x / 512, c = blockIdx.x % 512;
   const float a = sc[g * 512 + c], b = sh[g * 512 + c];
@@ -35,22 +36,22 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
     const int j = j0 + lane;
     float cs = 0.f;
     for (int i = warp; i < N; i += nw) {
-      if (j < M) cs += fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f);
+      if (j < M) { const float r = fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f); cs = mx ? fmaxf(cs, r) : cs + r; }
     }
     if (j < M) colacc[warp * M + j] = cs;
   }
   for (int i = warp; i < N; i += nw) {
     float rs = 0.f;
-    for (int j = lane; j < M; j += 32) rs += fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f);
+    for (int j = lane; j < M; j += 32) { const float r = fmaxf(fmaf(src[(long)i * M + j], a, b), 0.f); rs = mx ? fmaxf(rs, r) : rs + r; }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-    if (lane == 0) vout[M + i] = rs / (float)M;
+    for (int o = 16; o; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, rs, o); rs = mx ? fmaxf(rs, t) : rs + t; }
+    if (lane == 0) vout[M + i] = mx ? rs : rs / (float)M;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < M; j += blockDim.x) {
     float t = 0.f;
-    for (int w2 = 0; w2 < nw; w2++) t += colacc[w2 * M + j];
-    vout[j] = t / (float)N;
+    for (int w2 = 0; w2 < nw; w2++) t = mx ? fmaxf(t, colacc[w2 * M + j]) : t + colacc[w2 * M + j];
+    vout[j] = mx ? t : t / (float)N;
   }
 }
 
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
 // (coalesced 1 KB per row), 8 independent loads in flight per thread, fixed summation order.
 __global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __restrict__ y, long ld, int coff,
                                                              const float* __restrict__ sc, const float* __restrict__ sh,
-                                                             int N, int M, long ldv, float* __restrict__ V) {
+                                                             int N, int M, long ldv, float* __restrict__ V, int mx) {
   const int g = blockIdx.x / (N + M), r = blockIdx.x % (N + M);
   const bool is_end = r < N;
   const int cnt = is_end ? M : N;
@@ -77,11 +78,19 @@ __global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __rest
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) v[u] = __ldg(p + (long)(k + u) * step);
+      if (mx) {
 #pragma unroll
-      for (int u = 0; u < 8; u++) acc += fmaxf(fmaf(v[u], a, b), 0.f);
+        for (int u = 0; u < 8; u++) acc = fmaxf(acc, fmaf(v[u], a, b));     // acc starts at 0: max(relu(.))
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += fmaxf(fmaf(v[u], a, b), 0.f);
+      }
     }
-    for (; k < cnt; k++) acc += fmaxf(fmaf(__ldg(p + (long)k * step), a, b), 0.f);
-    V[(long)c * ldv + (long)g * (M + N) + (is_end ? M + r : r - N)] = acc / (float)cnt;
+    for (; k < cnt; k++) {
+      const float r2 = fmaxf(fmaf(__ldg(p + (long)k * step), a, b), 0.f);
+      acc = mx ? fmaxf(acc, r2) : acc + r2;
+    }
+    V[(long)c * ldv + (long)g * (M + N) + (is_end ? M + r : r - N)] = mx ? acc : acc / (float)cnt;
   }
 }
 // z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : one warp per row (a lane owns 4 channels: one coalesced 512-byte
@@ -269,12 +278,13 @@ extern "C" size_t mmmot_affinity_workspace(int pairs, int n, int m) {
   return a.off;
 }
 
-extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode, int pairs,
+extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int softmax_mode, int end_mode, int pairs,
                                   int n, int m, const float* feats, float* link, float* new_s,
                                   float* end_s, void* workspace, size_t workspace_bytes, void* stream) {
   if (!wts || !feats || !link || !new_s || !end_s || !workspace || pairs <= 0 || n <= 0 || m <= 0)
     return MMMOT_E_ARG;
-  if (affinity_op < 0 || affinity_op > MMMOT_AFF_MINUS || softmax_mode < 0 || softmax_mode > MMMOT_SM_DUAL_MAX)
+  if (affinity_op < 0 || affinity_op > MMMOT_AFF_MINUS || softmax_mode < 0 || softmax_mode > MMMOT_SM_DUAL_MAX ||
+      end_mode < MMMOT_END_AVG || end_mode > MMMOT_END_MAX)
     return MMMOT_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   MmArena ar(workspace, workspace_bytes);
@@ -329,12 +339,12 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   const long ldv = (long)G * (n + m);
   if (use_tc) {
     if (timed) mm_timing_begin(st, MM_T_AFF_MEAN, 0.0, 4.0 * 512 * (double)G * NM);
-    newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v);
+    newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v, end_mode);
     MM_LAUNCH_CHECK();
     if (timed) mm_timing_end(st);
   } else {
     rowcol_mean_kernel<<<G * 512, 256, 8 * m * sizeof(float), st>>>(w.y01 + 512L * NM, 1024L * NM, w.sc0, w.sh0,
-                                                               n, m, ldv, w.v);
+                                                               n, m, ldv, w.v, end_mode);
     MM_LAUNCH_CHECK();
   }
   const int tn = mm_cdiv(n, 128), tm_ = mm_cdiv(m, 128), ne_tiles = G * (tn + tm_);

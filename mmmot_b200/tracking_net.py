@@ -71,7 +71,7 @@ class TrackingNet(nn.Module):
         if appear_len != 512 or point_len != 512: unsupported.append("appear_len/point_len != 512")
         if appear_arch != 'vgg' or not appear_skippool or appear_fpn: unsupported.append("appearance must be vgg + skippool")
         if point_arch != 'v1' or not without_reflectivity: unsupported.append("point_arch must be v1 on xyz points")
-        if end_arch != 'v2' or end_mode != 'avg': unsupported.append("end_arch/end_mode must be v2/avg")
+        if end_arch != 'v2' or end_mode not in _lib.END_MODE: unsupported.append("end_arch must be v2, end_mode avg or max")
         if score_arch not in ('branch_cls', 'branch_reg'): unsupported.append("score_arch must be branch_cls/branch_reg")
         if score_fusion_arch not in _lib.FUSION: unsupported.append(f"score_fusion_arch {score_fusion_arch!r}")
         if affinity_op not in _lib.AFFINITY: unsupported.append(f"affinity_op {affinity_op!r}")
@@ -83,6 +83,7 @@ class TrackingNet(nn.Module):
         self.test_mode = test_mode          # 0:image; 1:LiDAR; 2:fusion (tracking_net.py:40)
         self.softmax_mode = softmax_mode
         self.affinity_op = affinity_op
+        self.end_mode = end_mode
         self.score_fusion_arch = score_fusion_arch
         # dropblock / use_dropout are identity in eval mode; accepted for config compatibility
         self.dropblock, self.use_dropout = dropblock, use_dropout
@@ -152,7 +153,7 @@ class TrackingNet(nn.Module):
                                             float(self.neg_threshold), pairs, L, vp(feats),
                                             vp(out["det"][p0:p0 + pairs]), wsp, wsn, st), "mmmot_fusion_det_fwd")
         _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op],
-                                          _lib.SOFTMAX.get(self.softmax_mode, 0), pairs, n, m, vp(feats),
+                                          _lib.SOFTMAX.get(self.softmax_mode, 0), _lib.END_MODE[self.end_mode], pairs, n, m, vp(feats),
                                           vp(out["link"][p0:p0 + pairs]), vp(out["new"][p0:p0 + pairs]),
                                           vp(out["end"][p0:p0 + pairs]), wsp, wsn, st), "mmmot_affinity_fwd")
         # the status word (FP16 range flag) of this chunk, accumulated into out["status"] in stream order
@@ -260,7 +261,7 @@ class TrackingNet(nn.Module):
             st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.mmmot_status_reset(vp(ws), st), "mmmot_status_reset")
             _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op],
-                                              _lib.SOFTMAX.get(self.softmax_mode, 0), B, n, m, vp(feats),
+                                              _lib.SOFTMAX.get(self.softmax_mode, 0), _lib.END_MODE[self.end_mode], B, n, m, vp(feats),
                                               vp(link), vp(new), vp(end), vp(ws), ws.numel(), st),
                        "mmmot_affinity_fwd")
             _lib.check(lib.mmmot_status_check(vp(ws), st), "mmmot_affinity_fwd")
@@ -344,7 +345,7 @@ class TrackingNet(nn.Module):
                                                 wsp, wsn, st), "mmmot_fusion_det_fwd")
             _lib.check(lib.mmmot_w_det_train_fwd(wts.ptr, L, vp(feats), vp(det), vp(bn_det), wsp, wsn, st), "mmmot_w_det_train_fwd")
             _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op], _lib.SOFTMAX.get(self.softmax_mode, 0),
-                                              1, n, m, vp(feats), vp(link), vp(new), vp(end), wsp, wsn, st), "mmmot_affinity_fwd")
+                                              _lib.END_MODE[self.end_mode], 1, n, m, vp(feats), vp(link), vp(new), vp(end), wsp, wsn, st), "mmmot_affinity_fwd")
             _lib.check(lib.mmmot_status_check(wsp, st), "mmmot_b200.TrackingNet training forward")
         # running averages (reference: nn.BatchNorm2d / BatchNorm1d side effect of a training-mode forward)
         h, w_ = H, W
@@ -356,6 +357,57 @@ class TrackingNet(nn.Module):
         self._update_running("w_det.4", bn_det[1, 0, :256], bn_det[1, 1, :256], 3.0 * L)
         return det[0], [link[0]], new[0], end[0], [wts.trans1.unsqueeze(0).clone(), wts.trans2.unsqueeze(0).clone()]
 
+    @torch.no_grad()
+    def _forward_multi(self, dets, det_info, splits):
+        """Samples of more than two frames (reference modules/tracking_net.py:170-182; sample_max_len > 2): the feature
+        stages run once over all L detections of the sample (one GroupNorm domain, exactly like the reference), then
+        ``associate`` runs on every pair of consecutive frames.  (The association programme of such samples is a
+        min-cost flow; mmmot_b200.ortools_solve handles two-frame samples only.)"""
+        lib = _lib.load()
+        wts = self.prepared()
+        dev = wts.flat.device
+        L = sum(splits)
+        crops = dets.contiguous().float()
+        points = det_info['points'].reshape(-1, det_info['points'].shape[-1])[:, :3].contiguous().float()
+        split = det_info['points_split'].reshape(-1).detach().to("cpu", torch.int32).contiguous()
+        if crops.device != dev or points.device != dev or crops.shape[0] != L or split.numel() != L + 1 or min(splits) <= 0:
+            raise _lib.MmmotError("inputs do not match the module's device / dets_split")
+        H, W = crops.shape[-2:]
+        feats = torch.empty(1, 3, 512, L, device=dev)
+        det = torch.empty(1, 3, L, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        links, news, ends = [], [], []
+        with torch.cuda.device(dev):
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            need = max([lib.mmmot_appearance_workspace(L, H, W), lib.mmmot_pointnet_workspace(1, L, int(split[-1])),
+                        lib.mmmot_fusion_det_workspace(1, L)] +
+                       [lib.mmmot_affinity_workspace(1, a, b) for a, b in zip(splits[:-1], splits[1:])])
+            ws = self._workspace(need, dev)
+            wsp, wsn = vp(ws), ctypes.c_size_t(ws.numel())
+            _lib.check(lib.mmmot_status_reset(wsp, st), "mmmot_status_reset")
+            _lib.check(lib.mmmot_appearance_fwd(wts.ptr, vp(crops), L, H, W, L, vp(feats), wsp, wsn, st), "mmmot_appearance_fwd")
+            hs = split.numpy()
+            _lib.check(lib.mmmot_pointnet_fwd(wts.ptr, vp(points), vp(split.to(dev)), ctypes.c_void_p(hs.ctypes.data), 1, L,
+                                              vp(feats), wsp, wsn, st), "mmmot_pointnet_fwd")
+            _lib.check(lib.mmmot_fusion_det_fwd(wts.ptr, _lib.FUSION[self.score_fusion_arch], self._score_flags(),
+                                                float(self.neg_threshold), 1, L, vp(feats), vp(det), wsp, wsn, st),
+                       "mmmot_fusion_det_fwd")
+            start = 0
+            for a, b in zip(splits[:-1], splits[1:]):
+                f = feats[:, :, :, start:start + a + b].contiguous()
+                link = torch.empty(1, 3, a, b, device=dev)
+                new = torch.empty(1, 3, b, device=dev)
+                end = torch.empty(1, 3, a, device=dev)
+                _lib.check(lib.mmmot_affinity_fwd(wts.ptr, _lib.AFFINITY[self.affinity_op], _lib.SOFTMAX.get(self.softmax_mode, 0),
+                                                  _lib.END_MODE[self.end_mode], 1, a, b, vp(f), vp(link), vp(new), vp(end),
+                                                  wsp, wsn, st), "mmmot_affinity_fwd")
+                links.append(link[0]); news.append(new[0]); ends.append(end[0])
+                start += a
+            _lib.check(lib.mmmot_status_check(wsp, st), "mmmot_b200.TrackingNet forward")
+        new_scores = torch.cat([det.new_zeros(3, splits[0])] + news, dim=1)        # tracking_net.py:183-189
+        end_scores = torch.cat(ends + [det.new_zeros(3, splits[-1])], dim=1)
+        return det[0], links, new_scores, end_scores, [wts.trans1.unsqueeze(0).clone(), wts.trans2.unsqueeze(0).clone()]
+
     def forward(self, dets, det_info, dets_split):
         """Reference signature (modules/tracking_net.py:165): one frame-pair.
 
@@ -365,9 +417,8 @@ class TrackingNet(nn.Module):
         training branch is returned instead (see _forward_train)."""
         if self.training:
             return self._forward_train(dets, det_info, dets_split)
-        if len(dets_split) != 2:
-            raise NotImplementedError("mmmot_b200.TrackingNet supports 2-frame samples (sample_max_len: 2), "
-                                      "the only case the reference's configs run (SURVEY F9)")
+        if len(dets_split) > 2:
+            return self._forward_multi(dets, det_info, [int(s) for s in dets_split])
         n, m = int(dets_split[0]), int(dets_split[1])
         split = det_info['points_split'].reshape(-1)
         o = self.forward_batch(dets, det_info['points'].reshape(-1, det_info['points'].shape[-1])[:, :3],
