@@ -218,17 +218,19 @@ int mmmot_lp_assign(const float* det, long det_stride, const float* link, long l
  * Per-detection LiDAR cropping (SURVEY.md 8f row N1 — the step right before the hot path).
  * Replaces the host loop of reference point_cloud/preprocess.py:72-81 / box_np_ops.py:688-699 /
  * geometry.py:96-114.  planes[n_boxes][6][4]: inward plane equations (nx, ny, nz, d) of each rotated box,
- * prepared by the host exactly as the reference's numpy code does (mmmot_b200/lidar_crop.py); a point is inside
- * iff x*nx + y*ny + z*nz + d < 0 for all six (evaluated in the reference's FP32 operation order, unfused).
+ * prepared by the host exactly as the reference's numpy code does (mmmot_b200/lidar_crop.py), float64 when
+ * planes_f64 != 0 (the reference's real pipeline: box_camera_to_lidar yields float64 boxes) else float32; a point is
+ * inside iff x*nx + y*ny + z*nz + d < 0 for all six (evaluated in that precision, in the reference's operation
+ * order, unfused).
  * Two steps because the output size is data dependent:
  *   mmmot_crop_count   -> split[n_boxes + 1] (device) CSR offsets; an empty box counts one (zero) point
  *   mmmot_crop_scatter -> out_points[split[n_boxes]][out_channels], scene order preserved inside a box
  * Both need the same workspace (mmmot_crop_workspace bytes) and the count step's contents are consumed by scatter.
  */
 size_t mmmot_crop_workspace(int n_points, int n_boxes);
-int mmmot_crop_count(const float* points, int n_points, int stride, const float* planes, int n_boxes,
+int mmmot_crop_count(const float* points, int n_points, int stride, const void* planes, int planes_f64, int n_boxes,
                      int* split, void* workspace, size_t workspace_bytes, void* stream);
-int mmmot_crop_scatter(const float* points, int n_points, int stride, const float* planes, int n_boxes,
+int mmmot_crop_scatter(const float* points, int n_points, int stride, const void* planes, int planes_f64, int n_boxes,
                        const int* split, int out_channels, float* out_points, void* workspace,
                        size_t workspace_bytes, void* stream);
 

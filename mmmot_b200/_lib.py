@@ -78,8 +78,8 @@ SIGNATURES = {
     "mmmot_affinity_workspace": (_sz, [_i, _i, _i]),
     "mmmot_affinity_fwd": (_i, [_wp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_crop_workspace": (_sz, [_i, _i]),
-    "mmmot_crop_count": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
-    "mmmot_crop_scatter": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "mmmot_crop_count": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "mmmot_crop_scatter": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "mmmot_crop_resize_max_taps": (_i, []),
     "mmmot_crop_resize_workspace": (_sz, [_i, _l, _i, _i]),
     "mmmot_crop_resize": (_i, [_vp, _i, _i, _vp, _vp, _i, _l, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -4,8 +4,11 @@
 //
 // The six inward-facing plane equations of every rotated box are prepared on the host exactly as the
 // reference's numpy code computes them (mmmot_b200/lidar_crop.py); the kernels evaluate the reference's
-// membership predicate  sign = x*nx + y*ny + z*nz + d ; inside <=> sign < 0 for all 6 planes  in FP32 with the
-// same operation order and NO fused multiply-add, so membership is bit-identical to the reference.
+// membership predicate  sign = x*nx + y*ny + z*nz + d ; inside <=> sign < 0 for all 6 planes  with the same
+// operation order and NO fused multiply-add, in the precision of the plane equations: float64 in the reference's
+// real pipeline (box_camera_to_lidar promotes the boxes to float64, box_np_ops.py:584-589, so numba evaluates the
+// predicate in float64 on the float32 points), float32 when the caller hands float32 boxes.  Membership is
+// bit-identical to the reference in both cases.
 // Output = the packed per-detection point list + CSR offsets that mmmot_pointnet_fwd consumes; point order
 // inside a detection is the scene order (stable compaction); an empty box yields one all-zero point
 // (preprocess.py:78-79).
@@ -26,12 +29,24 @@ __device__ __forceinline__ bool inside_box(const float* __restrict__ pl, float x
   }
   return true;
 }
+__device__ __forceinline__ bool inside_box(const double* __restrict__ pl, float xf, float yf, float zf) {
+  const double x = xf, y = yf, z = zf;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double s = __dadd_rn(__dmul_rn(x, pl[4 * k]), __dmul_rn(y, pl[4 * k + 1]));
+    s = __dadd_rn(s, __dmul_rn(z, pl[4 * k + 2]));
+    s = __dadd_rn(s, pl[4 * k + 3]);
+    if (s >= 0.0) return false;
+  }
+  return true;
+}
 
 // counts[b][tile] = number of points of the tile inside box b
+template <typename T>
 __global__ void __launch_bounds__(kTile) crop_count_kernel(const float* __restrict__ pts, int stride, int P,
-                                                           const float* __restrict__ planes, int tiles,
+                                                           const T* __restrict__ planes, int tiles,
                                                            int* __restrict__ counts) {
-  __shared__ float pl[24];
+  __shared__ T pl[24];
   const int b = blockIdx.y, tile = blockIdx.x;
   if (threadIdx.x < 24) pl[threadIdx.x] = planes[b * 24 + threadIdx.x];
   __syncthreads();
@@ -84,12 +99,13 @@ __global__ void crop_scan_boxes_kernel(const int* __restrict__ totals, int n, in
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kTile) crop_scatter_kernel(const float* __restrict__ pts, int stride, int P,
-                                                             const float* __restrict__ planes, int tiles,
+                                                             const T* __restrict__ planes, int tiles,
                                                              const int* __restrict__ tile_off,
                                                              const int* __restrict__ split, int out_c,
                                                              float* __restrict__ out) {
-  __shared__ float pl[24];
+  __shared__ T pl[24];
   __shared__ int wcnt[kTile / 32];
   const int b = blockIdx.y, tile = blockIdx.x;
   if (threadIdx.x < 24) pl[threadIdx.x] = planes[b * 24 + threadIdx.x];
@@ -128,15 +144,18 @@ extern "C" size_t mmmot_crop_workspace(int n_points, int n_boxes) {
   return mm_align(tiles * n_boxes * sizeof(int)) + mm_align((size_t)n_boxes * sizeof(int));
 }
 
-extern "C" int mmmot_crop_count(const float* points, int n_points, int stride, const float* planes, int n_boxes,
-                                int* split, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int mmmot_crop_count(const float* points, int n_points, int stride, const void* planes, int planes_f64,
+                                int n_boxes, int* split, void* workspace, size_t workspace_bytes, void* stream) {
   if (!points || !planes || !split || !workspace || n_points <= 0 || n_boxes <= 0 || stride < 3) return MMMOT_E_ARG;
   if (workspace_bytes < mmmot_crop_workspace(n_points, n_boxes)) return MMMOT_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = mm_cdiv(n_points, kTile);
   int* counts = (int*)workspace;
   int* totals = (int*)((char*)workspace + mm_align((size_t)tiles * n_boxes * sizeof(int)));
-  crop_count_kernel<<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, planes, tiles, counts);
+  if (planes_f64)
+    crop_count_kernel<double><<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, (const double*)planes, tiles, counts);
+  else
+    crop_count_kernel<float><<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, (const float*)planes, tiles, counts);
   MM_LAUNCH_CHECK();
   crop_scan_tiles_kernel<<<n_boxes, 256, 0, st>>>(counts, tiles, totals);
   MM_LAUNCH_CHECK();
@@ -145,8 +164,8 @@ extern "C" int mmmot_crop_count(const float* points, int n_points, int stride, c
   return 0;
 }
 
-extern "C" int mmmot_crop_scatter(const float* points, int n_points, int stride, const float* planes, int n_boxes,
-                                  const int* split, int out_channels, float* out_points, void* workspace,
+extern "C" int mmmot_crop_scatter(const float* points, int n_points, int stride, const void* planes, int planes_f64,
+                                  int n_boxes, const int* split, int out_channels, float* out_points, void* workspace,
                                   size_t workspace_bytes, void* stream) {
   if (!points || !planes || !split || !out_points || !workspace || n_points <= 0 || n_boxes <= 0) return MMMOT_E_ARG;
   if (out_channels < 3 || out_channels > 4 || out_channels > stride) return MMMOT_E_ARG;
@@ -155,8 +174,12 @@ extern "C" int mmmot_crop_scatter(const float* points, int n_points, int stride,
   const int tiles = mm_cdiv(n_points, kTile);
   const int* tile_off = (const int*)workspace;
   const int* totals = (const int*)((const char*)workspace + mm_align((size_t)tiles * n_boxes * sizeof(int)));
-  crop_scatter_kernel<<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, planes, tiles, tile_off, split,
-                                                              out_channels, out_points);
+  if (planes_f64)
+    crop_scatter_kernel<double><<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, (const double*)planes, tiles,
+                                                                        tile_off, split, out_channels, out_points);
+  else
+    crop_scatter_kernel<float><<<dim3(tiles, n_boxes), kTile, 0, st>>>(points, stride, n_points, (const float*)planes, tiles,
+                                                                       tile_off, split, out_channels, out_points);
   MM_LAUNCH_CHECK();
   crop_fill_empty_kernel<<<mm_cdiv(n_boxes, 128), 128, 0, st>>>(totals, split, n_boxes, out_channels, out_points);
   MM_LAUNCH_CHECK();

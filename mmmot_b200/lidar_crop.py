@@ -8,7 +8,9 @@ all-zero point, and the result is the packed ``points`` + ``points_split`` pair 
 ``TrackingNet.forward`` / ``forward_batch`` take.
 
 The box -> plane-equation preparation (n boxes x 6 planes, microseconds of host work) is done with the
-same numpy operations as the reference so that the float32 plane coefficients are identical; the
+same numpy operations, in the same dtype, as the reference so that the plane coefficients are identical
+(float64 for boxes coming from ``box_camera_to_lidar`` — the reference's real pipeline, where ``np.ones``
+promotes them — float32 for float32 boxes); the
 O(P x n) membership test and the stable compaction run in libmmmot_sm100a.so (csrc/lidar_crop.cu).
 There is no CPU path for the membership test.
 """
@@ -38,9 +40,9 @@ def box_camera_to_lidar(boxes_cam, r_rect, velo2cam):
 
 def box_planes(boxes_lidar):
     """[n][7] LiDAR-frame boxes (x, y, z, w, l, h, yaw; origin (0.5, 0.5, 0), rotation about z) ->
-    float32 [n][6][4] inward plane equations (nx, ny, nz, d).  Same numpy operations, in the same order,
-    as reference box_np_ops.py:147-178 (corners), :236-254 (rotation), :312-337, :702-720 (faces) and
-    geometry.py:84-93 (plane equations), so the float32 results are identical."""
+    [n][6][4] inward plane equations (nx, ny, nz, d) in the boxes' dtype (float32 or float64).  Same numpy
+    operations, in the same order, as reference box_np_ops.py:147-178 (corners), :236-254 (rotation), :312-337,
+    :702-720 (faces) and geometry.py:84-93 (plane equations), so the results are identical."""
     rb = np.asarray(boxes_lidar)
     centers, dims, angles = rb[:, :3], rb[:, 3:6], rb[:, 6]
     unit = np.stack(np.unravel_index(np.arange(8), [2] * 3), axis=1).astype(dims.dtype)[_CORNER_ORDER]
@@ -55,7 +57,7 @@ def box_planes(boxes_lidar):
     vec = surf[:, :, :2, :] - surf[:, :, 1:3, :]
     normal = np.cross(vec[:, :, 0, :], vec[:, :, 1, :])
     d = -np.einsum('aij, aij->ai', normal, surf[:, :, 0, :])
-    return np.concatenate([normal, d[..., None]], axis=-1).astype(np.float32)
+    return np.concatenate([normal, d[..., None]], axis=-1).astype(rb.dtype if rb.dtype == np.float64 else np.float32)
 
 
 def crop_points(points, boxes_lidar, without_reflectivity=True):
@@ -67,7 +69,9 @@ def crop_points(points, boxes_lidar, without_reflectivity=True):
         raise _lib.MmmotError("mmmot_b200.crop_points runs on CUDA only (no CPU fallback)")
     points = points.contiguous().float()
     P, C = points.shape
-    boxes = np.asarray(boxes_lidar, dtype=np.float32).reshape(-1, 7)
+    boxes = np.asarray(boxes_lidar)
+    f64 = boxes.dtype == np.float64         # the reference evaluates the predicate in the boxes' precision
+    boxes = boxes.astype(np.float64 if f64 else np.float32).reshape(-1, 7)
     n = boxes.shape[0]
     dev = points.device
     with torch.cuda.device(dev):            # the library works on the CURRENT device
@@ -76,10 +80,10 @@ def crop_points(points, boxes_lidar, without_reflectivity=True):
         split = torch.empty(n + 1, dtype=torch.int32, device=dev)
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(lib.mmmot_crop_count(vp(points), P, C, vp(planes), n, vp(split), vp(ws), ws.numel(), st), "mmmot_crop_count")
+        _lib.check(lib.mmmot_crop_count(vp(points), P, C, vp(planes), int(f64), n, vp(split), vp(ws), ws.numel(), st), "mmmot_crop_count")
         split_h = split.cpu()                      # output size is data dependent: one sync, like the reference's host loop
         out_c = 3 if without_reflectivity else min(C, 4)
         out = torch.empty(int(split_h[-1]), out_c, device=dev)
-        _lib.check(lib.mmmot_crop_scatter(vp(points), P, C, vp(planes), n, vp(split), out_c, vp(out), vp(ws), ws.numel(), st),
+        _lib.check(lib.mmmot_crop_scatter(vp(points), P, C, vp(planes), int(f64), n, vp(split), out_c, vp(out), vp(ws), ws.numel(), st),
                    "mmmot_crop_scatter")
     return out, split_h.long()

@@ -12,9 +12,12 @@ from mmmot_b200.lidar_crop import box_planes
 
 
 def points_in_boxes(points, boxes_lidar):
-    """bool [P][n]: sign = x*nx + y*ny + z*nz + d evaluated left to right in float32 (geometry.py:108-113)."""
-    pl = box_planes(np.asarray(boxes_lidar, dtype=np.float32))          # [n][6][4]
-    p = np.asarray(points, dtype=np.float32)
+    """bool [P][n]: sign = x*nx + y*ny + z*nz + d evaluated left to right (geometry.py:108-113) in the precision numba
+    gives it: float64 when the boxes are float64 (the real pipeline, box_np_ops.py:584-589), float32 otherwise."""
+    b = np.asarray(boxes_lidar)
+    dt = np.float64 if b.dtype == np.float64 else np.float32
+    pl = box_planes(b.astype(dt))                                        # [n][6][4]
+    p = np.asarray(points, dtype=np.float32).astype(dt)
     x, y, z = p[:, None, None, 0], p[:, None, None, 1], p[:, None, None, 2]
     s = (x * pl[None, :, :, 0] + y * pl[None, :, :, 1]) + z * pl[None, :, :, 2]
     s = s + pl[None, :, :, 3]

@@ -81,8 +81,20 @@ def crop_goldens():
         cam = np.concatenate([rng.uniform([-20, 0, 5], [20, 2, 60], size=(n, 3)), rng.uniform(1, 4, size=(n, 3)),
                               rng.uniform(-3, 3, size=(n, 1))], 1).astype(np.float32)
         lid = box_np_ops.box_camera_to_lidar(cam, rect, v2c)
+        # the reference's real pipeline: float64 boxes out of box_camera_to_lidar -> float64 predicate (numba).
+        # Boxes: the same ones, moved camera -> LiDAR in float64 like preprocess.py:72-75 does
+        boxes64 = boxes.astype(np.float64) + rng.uniform(-1e-7, 1e-7, size=boxes.shape)      # genuinely float64 values
+        out64, split64 = [], [0]
+        for i in range(n):
+            bp = remove_points_outside_boxes(pts, boxes64[i:i + 1])
+            if bp.shape[0] == 0:
+                bp = np.zeros((1, 4))
+            split64.append(split64[-1] + bp.shape[0])
+            out64.append(bp)
+        out64 = np.concatenate(out64, 0)[:, :3].astype(np.float32)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), points=pts, boxes=boxes, out=out,
-                            split=np.asarray(split, np.int64), rect=rect, v2c=v2c, cam=cam, lidar=lid)
+                            split=np.asarray(split, np.int64), rect=rect, v2c=v2c, cam=cam, lidar=lid,
+                            boxes64=boxes64, out64=out64, split64=np.asarray(split64, np.int64))
         print(name, out.shape, split[-1])
 
 

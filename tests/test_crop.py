@@ -18,7 +18,10 @@ def test_oracle_matches_reference_golden(path):
     g = np.load(path)
     out, split = crop_points_ref(g["points"], g["boxes"])
     assert np.array_equal(split, g["split"]) and np.array_equal(out, g["out"])          # bit-exact
-    assert np.array_equal(box_camera_to_lidar(g["cam"], g["rect"], g["v2c"]), g["lidar"])
+    lid = box_camera_to_lidar(g["cam"], g["rect"], g["v2c"])
+    assert lid.dtype == np.float64 and np.array_equal(lid, g["lidar"])                  # promoted like the reference
+    out, split = crop_points_ref(g["points"], g["boxes64"])                             # float64 boxes: float64 predicate
+    assert np.array_equal(split, g["split64"]) and np.array_equal(out, g["out64"])
 
 
 def test_plane_normals_point_inward():
@@ -36,6 +39,8 @@ def test_gpu_crop_matches_reference_golden(path):
     out, split = mmmot_b200.crop_points(torch.from_numpy(g["points"]).cuda(), g["boxes"])
     assert torch.equal(split, torch.from_numpy(g["split"]))
     assert torch.equal(out.cpu(), torch.from_numpy(g["out"]))                            # membership + order bit-exact
+    out, split = mmmot_b200.crop_points(torch.from_numpy(g["points"]).cuda(), g["boxes64"])   # the float64 pipeline
+    assert torch.equal(split, torch.from_numpy(g["split64"])) and torch.equal(out.cpu(), torch.from_numpy(g["out64"]))
 
 
 @pytest.mark.gpu
