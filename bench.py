@@ -407,10 +407,6 @@ def main():
     # mirrored to pinned host memory for the end-to-end leg
     h_crops = torch.empty(crops.shape, dtype=torch.float32, pin_memory=True).copy_(crops)
     h_points = torch.empty(points.shape, dtype=torch.float32, pin_memory=True).copy_(points)
-    h_match = torch.empty(B, n, dtype=torch.int32, pin_memory=True)
-    h_flags = torch.empty(3, B, L, dtype=torch.float32, pin_memory=True)
-    h_status = torch.zeros(8, dtype=torch.int32, pin_memory=True)
-    d_crops2, d_points2 = torch.empty_like(crops), torch.empty_like(points)
 
     last = {}
 
@@ -423,42 +419,16 @@ def main():
         last["status"] = o["status"]
         return o
 
-    # e2e: pinned host -> device copies are pipelined against compute in sub-batches (copy stream + events);
-    # every byte of every step's inputs crosses PCIe inside the timed region, results come back D2H.
-    nsub = 4 if B % 4 == 0 and B >= 8 else 1
-    sb = B // nsub
-    copy_stream = torch.cuda.Stream(device=dev)
-    ev_copied = [torch.cuda.Event() for _ in range(nsub)]
-    ev_used = [torch.cuda.Event() for _ in range(nsub)]
-    sub_split = torch.arange(0, sb * L * pts + 1, pts, dtype=torch.int32)
-    for e in ev_used:
-        e.record()
+    # e2e = the package's own host pipeline (mmmot_b200.HostPipeline): pinned host -> device copies overlapped with
+    # compute in sub-batches, results device -> host; every byte of every step's inputs crosses PCIe inside the timed
+    # region.
+    pipe = mmmot_b200.HostPipeline(net, n, sub_batches=4)
 
     def step_e2e():
-        cur = torch.cuda.current_stream(dev)
-        for i in range(nsub):
-            c0, c1 = i * sb * L, (i + 1) * sb * L
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_used[i])             # previous step finished reading this slice
-                d_crops2[c0:c1].copy_(h_crops[c0:c1], non_blocking=True)
-                d_points2[c0 * pts:c1 * pts].copy_(h_points[c0 * pts:c1 * pts], non_blocking=True)
-                ev_copied[i].record(copy_stream)
-        outs = []
-        for i in range(nsub):
-            c0, c1 = i * sb * L, (i + 1) * sb * L
-            cur.wait_event(ev_copied[i])
-            o = net.predict_batch(d_crops2[c0:c1], d_points2[c0 * pts:c1 * pts], sub_split, n, check=False)
-            ev_used[i].record(cur)
-            p0, p1 = i * sb, (i + 1) * sb
-            h_match[p0:p1].copy_(o["match"], non_blocking=True)
-            h_flags[0, p0:p1].copy_(o["assign_det"], non_blocking=True)
-            h_flags[1, p0:p1].copy_(o["assign_new"], non_blocking=True)
-            h_flags[2, p0:p1].copy_(o["assign_end"], non_blocking=True)
-            h_status[i:i + 1].copy_(o["status"], non_blocking=True)     # the library's range flag travels with the results
-            outs.append(o["match"])
+        r = pipe.run(h_crops, h_points, split, sync=False)
         if world > 1:
-            gather_pairs(torch.cat(outs, 0), total)
-        return outs
+            gather_pairs(r["match_device"], total)
+        return r
 
     def timed(fn, steps, warmup, with_hooks=False):
         for _ in range(warmup):
@@ -503,7 +473,7 @@ def main():
         sampler2.start()
     ms_e2e, _, _ = timed(step_e2e, args.steps, warm)
     clocks_e2e = sampler2.summary() if sampler2 else None
-    status |= int(h_status.max())
+    status |= int(pipe.h_status.max())
 
     # N-GPU result == 1-GPU result: rank 0 recomputes rank 1's shard from the same seeded inputs and compares it bit
     # for bit with what the gather returned (outside the timed region)
@@ -551,8 +521,7 @@ def main():
         cpu = None
         if not args.no_cpu and world == 1:      # the CPU baseline is reported at N=1 only
             cpu, _, _ = cpu_leg(c, args.cpu_pairs)
-        h2d = h_crops.numel() * 4 + h_points.numel() * 4 + split.numel() * 4
-        d2h = h_match.numel() * 4 + h_flags.numel() * 4 + nsub * 4
+        h2d, d2h = pipe.bytes_per_batch(h_crops, h_points, split)
         line = {"metric": metric_name(c), "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None,

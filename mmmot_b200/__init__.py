@@ -7,6 +7,7 @@ from .lidar_crop import box_camera_to_lidar, box_planes, crop_points  # noqa: F4
 from .image_crop import crop_boxes, crop_resize  # noqa: F401
 from .tracking_model import TrackingModule, kitti_result_line, write_kitti_result  # noqa: F401
 from .cost import DetLoss, LinkLoss, TrackingLoss  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
 
 def set_engine(engine):
