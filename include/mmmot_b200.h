@@ -103,7 +103,10 @@ enum mmmot_weight_id {
   MMMOT_W_VGG_BNW0 = 187,         /* .. +12 : BatchNorm2d weight */
   MMMOT_W_VGG_BNB0 = 200,         /* .. +12 : BatchNorm2d bias */
   MMMOT_W_WD_RAW0 = 213,          /* .. +7  : w_det w1t b1 bn1_w bn1_b w2t b2 bn2_w bn2_b */
-  MMMOT_W_COUNT = 221
+  /* ---- packed tensor-core tiles of the per-detection contractions (fusion linears, gates, w_det; BN folded) */
+  MMMOT_W_FU_WPP = 221, MMMOT_W_FU_WIP = 222, MMMOT_W_FU_GATE_PP = 223, MMMOT_W_FU_GATE_IP = 224,
+  MMMOT_W_WD_W1P = 225, MMMOT_W_WD_W2P = 226,
+  MMMOT_W_COUNT = 227
 };
 
 typedef struct mmmot_weights {

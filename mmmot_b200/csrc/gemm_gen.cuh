@@ -6,7 +6,8 @@
 //   GEN_PAIR_*  the two feature slabs of the frame-pair:  x[(i,j)][k] = f[i][k] (*|-) f[N+j][k]   (reference
 //               modules/gcn.py:6-41; the 3 x 512 x N x M tensor is never stored), or
 //   GEN_NORM    the previous layer's fp32 output:  x[s][k] = relu(y[s][k]*sc[g][k] + sh[g][k])   (GroupNorm + ReLU of
-//               the producer layer applied on the fly; no normalised copy of the activation is ever written).
+//               the producer layer applied on the fly; no normalised copy of the activation is ever written), or
+//   GEN_COPY    an fp32 channels-last activation as it is (the small per-detection contractions: fusion, w_det).
 // All activations are channels-last ([row][channel]).  A producer thread owns one 8-wide k group of four columns per
 // chunk: one 256-bit load per (column, source) — a quarter warp reads eight rows, the four quarters the four k groups
 // of the same 128-byte lines — and one 16-byte shared-memory store per (column, plane); the epilogue writes a warp's
@@ -23,7 +24,7 @@ namespace gen {
 
 using namespace tc;
 
-enum { GEN_PAIR_MUL = 0, GEN_PAIR_ABS = 1, GEN_PAIR_SUB = 2, GEN_NORM = 3 };   // GEN_PAIR_* == MMMOT_AFF_*
+enum { GEN_PAIR_MUL = 0, GEN_PAIR_ABS = 1, GEN_PAIR_SUB = 2, GEN_NORM = 3, GEN_COPY = 4 };   // GEN_PAIR_* == MMMOT_AFF_*
 
 constexpr int G_EPI_WARPS = 8, G_MMA_WARP = 8, G_LOAD_WARP = 9, G_PROD_WARP0 = 10, G_PROD_WARPS = 8;
 constexpr int G_THREADS = (G_PROD_WARP0 + G_PROD_WARPS) * 32;   // 576
@@ -235,8 +236,9 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
     // the L2 transfer of one chunk overlaps the conversion of the previous one; the generic pairwise variant (8 source
     // vectors per chunk) has no registers for that and only overlaps its loads with the wait for the ring slot.
     constexpr bool PREFETCH = PAIRED;
-    constexpr int NA = (GEN == GEN_NORM || !PAIRED) ? 4 : 2;       // source vectors of 8 floats per chunk: a / y ...
-    constexpr int NB = GEN == GEN_NORM ? 0 : (PAIRED ? 2 : 4);     // ... and b
+    constexpr bool ROWS = GEN == GEN_NORM || GEN == GEN_COPY;      // the operand is a function of one fp32 source row
+    constexpr int NA = (ROWS || !PAIRED) ? 4 : 2;                  // source vectors of 8 floats per chunk: a / y ...
+    constexpr int NB = ROWS ? 0 : (PAIRED ? 2 : 4);                // ... and b
     const int pt = tid - G_PROD_WARP0 * 32;   // 0..255
     const int kg = (pt >> 3) & 3;
     const int cb = (pt & 7) + 8 * (pt >> 5);
@@ -250,14 +252,14 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
       tile_cols(nt, g, c0, len);
       unsigned okmask = 0;
       // 32-bit element offsets of the items' rows (this thread's k group) relative to the tile's / group's base
-      const float* tbase = GEN == GEN_NORM ? P.src + ((long)g * p.x_gs + c0) * P.ld_src : P.src + (long)g * P.Lf * p.K;
+      const float* tbase = ROWS ? P.src + ((long)g * p.x_gs + c0) * P.ld_src : P.src + (long)g * P.Lf * p.K;
       int oa[NA], ob[NB ? NB : 1];
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int col = cb + 64 * r;
         if (col < len) okmask |= 1u << r;
         const int cc = min(col, len - 1);
-        if (GEN == GEN_NORM) {
+        if (ROWS) {
           oa[r] = cc * P.ld_src + kg * 8;
         } else {
           const int s = c0 + cc;
@@ -307,6 +309,9 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
               x[2] = fmaxf(fmaf(y[2], sc0.z, sh0.z), 0.f); x[3] = fmaxf(fmaf(y[3], sc0.w, sh0.w), 0.f);
               x[4] = fmaxf(fmaf(y[4], sc1.x, sh1.x), 0.f); x[5] = fmaxf(fmaf(y[5], sc1.y, sh1.y), 0.f);
               x[6] = fmaxf(fmaf(y[6], sc1.z, sh1.z), 0.f); x[7] = fmaxf(fmaf(y[7], sc1.w, sh1.w), 0.f);
+            } else if (GEN == GEN_COPY) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) x[e] = R.a[r][e];
             } else {
               const float(&av)[8] = R.a[PAIRED ? (r >> 1) : r];
               const float(&bv)[8] = R.b[NB ? (PAIRED ? (r & 1) : r) : 0];
@@ -369,8 +374,9 @@ template <int GEN, bool PAIRED>
 static int gemm_gen_launch_t(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
                            const float* gsc, const float* gsh, int n, int m, int Lf, cudaStream_t st) {
   if (!Wp || !src || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
-  if (g.tile_tab && (GEN != gen::GEN_NORM || g.x_gs || g.y_gs)) return MMMOT_E_ARG;
-  if (GEN == gen::GEN_NORM && (g.K > gen::G_MAX_K || !gsc || !gsh || ld_src < g.K || (ld_src & 7))) return MMMOT_E_ARG;
+  if (g.tile_tab && ((GEN != gen::GEN_NORM && GEN != gen::GEN_COPY) || g.x_gs || g.y_gs)) return MMMOT_E_ARG;
+  if (GEN == gen::GEN_NORM && (g.K > gen::G_MAX_K || !gsc || !gsh)) return MMMOT_E_ARG;
+  if ((GEN == gen::GEN_NORM || GEN == gen::GEN_COPY) && (ld_src < g.K || (ld_src & 7))) return MMMOT_E_ARG;
   int sms = 0;
   MM_TRY(mm_sm_count(&sms));
   static std::atomic<unsigned long long> attr{0};
@@ -399,7 +405,7 @@ template <int GEN>
 static int gemm_gen_launch(const GemmP& g, const uint4* Wp, float out_scale, const float* src, int ld_src,
                            const float* gsc, const float* gsh, int n, int m, int Lf, cudaStream_t st) {
   // debug bit 10 (1024): producers without the software pipeline (A/B runs)
-  const bool pipe = !(mm_debug_flags() & 1024) && (GEN == gen::GEN_NORM ? (mm_debug_flags() & 4096) != 0 : m == 128);
+  const bool pipe = !(mm_debug_flags() & 1024) && (GEN == gen::GEN_NORM ? (mm_debug_flags() & 4096) != 0 : GEN == gen::GEN_COPY ? true : m == 128);
   if (pipe) return gemm_gen_launch_t<GEN, true>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, st);
   return gemm_gen_launch_t<GEN, false>(g, Wp, out_scale, src, ld_src, gsc, gsh, n, m, Lf, st);
 }
