@@ -197,7 +197,8 @@ def run_reference(args, c, name, rank):
     line = {"impl": "reference", "metric": metric_name(c), "value": cpu["value"], "unit": "frame-pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_dict(c, name, 1, 1, "weak"), note="CPU: one frame-pair per step (bounded sample of the same workload)"),
+            # the same config as the GPU arm; every CPU "step" is a bounded sample of it (cpu_baseline.sample)
+            "config": dict(config_dict(c, name, args.pairs or c["pairs"], max(args.gpus, 1), "weak"), engine="auto"),
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
