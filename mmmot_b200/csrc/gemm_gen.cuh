@@ -127,7 +127,7 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
         const int co = (mg * MT + mt) * 128 + q * 32 + lane;
         const bool rowok = co < p.M;
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
-        double d1 = 0.0, d2 = 0.0;
+        float f1 = 0.f, f2 = 0.f;   // (sum, sum of squares) over this thread's 128 columns: four fp32 chunk sums
         // channels-last: a warp's 32 consecutive channels of one column are one 128-byte line
         float* dst = p.Y + ((long)g * p.y_gs + c0 + half * 128) * p.y_ms + co;
 #pragma unroll 1
@@ -151,7 +151,7 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
               s1 += x; s2 = fmaf(x, x, s2);
             }
           }
-          d1 += (double)s1; d2 += (double)s2;
+          f1 += s1; f2 += s2;
           if (p.Y && rowok) {
             float* d = dst + (long)cc * 32 * p.y_ms;
             if (col0 + 32 <= len) {
@@ -164,7 +164,7 @@ static __global__ void __launch_bounds__(G_THREADS, 1) gemm_gen_kernel(const Gen
             }
           }
         }
-        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2(d1, d2);
+        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2((double)f1, (double)f2);
       }
       tc_fence_before();
       __syncwarp();

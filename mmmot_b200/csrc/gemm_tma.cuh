@@ -48,7 +48,30 @@ struct TmaP {
   unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
   int* status;              // workspace status word (FP16 range flag of the planar outputs) or null
+  const int4* chunk_tab;    // matrix mode with g.seg: per (column tile, half) the four 32-column chunks' descriptors
+                            // (first detection index << 1) | (chunk complete and inside ONE detection); see
+                            // seg_chunk_tab_kernel.  One uniform 16-byte load per subtile instead of a load + 12 shuffles.
 };
+
+// chunk descriptors of the table-tiled contractions over ragged per-detection columns (PointNet): tab[tile*2 + half]
+static __global__ void seg_chunk_tab_kernel(const int4* __restrict__ tiles, int num_tiles, const int* __restrict__ seg,
+                                            int4* __restrict__ tab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_tiles * 2) return;
+  const int4 tt = tiles[idx >> 1];
+  const int half = idx & 1, c0 = tt.y, len = tt.z;
+  int v[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int col0 = half * 128 + c * 32;
+    v[c] = 0;
+    if (col0 < len) {
+      const int first = seg[c0 + col0], last = seg[c0 + min(col0 + 31, len - 1)];
+      v[c] = (first << 1) | ((col0 + 32 <= len && first == last) ? 1 : 0);
+    }
+  }
+  tab[idx] = make_int4(v[0], v[1], v[2], v[3]);
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
   asm volatile(
@@ -325,26 +348,23 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
         const int co = (mg * MT + mt) * 128 + q * 32 + lane;
         const bool rowok = co < p.M;
         const float bv = (rowok && p.bias) ? __ldg(p.bias + co) : 0.f;
-        double d1 = 0.0, d2 = 0.0;
+        float f1 = 0.f, f2 = 0.f;   // this thread's (sum, sum of squares) over its 128 columns: four fp32 chunk sums
         const bool pass2 = P.segsum && !p.part && !p.Y && !p.relu;
         // Everything the four 32-column chunks need from global memory is fetched up front, so its latency is paid once
         // per subtile instead of once (or twice, seg -> addend) per chunk: the detection index at both ends of every
         // chunk (one load: lane 2c / 2c+1 holds chunk c's first / last column), the per-detection addend row of every
         // single-detection chunk, and the GroupNorm affine of the recomputing pass.
         const bool use_seg = p.seg && (p.addend || P.segsum);
-        int segv = 0;
-        if (use_seg && lane < 8) {
-          const int col = min(half * 128 + (lane >> 1) * 32 + ((lane & 1) ? 31 : 0), len - 1);
-          if (col >= 0) segv = __ldg(p.seg + c0 + col);
-        }
+        int4 ct = make_int4(0, 0, 0, 0);
+        if (use_seg) ct = __ldg(P.chunk_tab + (long)nt * 2 + half);   // same address in every lane: one transaction
+        const int cdesc[4] = {ct.x, ct.y, ct.z, ct.w};
         float adv[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned one_det = 0;   // bit c: chunk c is complete and lies inside one detection
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          const int da = __shfl_sync(0xffffffffu, segv, 2 * c), db = __shfl_sync(0xffffffffu, segv, 2 * c + 1);
-          if (use_seg && half * 128 + c * 32 + 32 <= len && da == db) {
+          if (cdesc[c] & 1) {
             one_det |= 1u << c;
-            if (p.addend && rowok) adv[c] = __ldg(p.addend + (long)da * p.ld_add + co);
+            if (p.addend && rowok) adv[c] = __ldg(p.addend + (long)(cdesc[c] >> 1) * p.ld_add + co);
           }
         }
         float na = 0.f, nb = 0.f;
@@ -353,7 +373,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
         for (int cc = 0; cc < 4; cc++) {
           const int col0 = half * 128 + cc * 32;
           if (col0 >= len) break;   // warp-uniform
-          const int da = __shfl_sync(0xffffffffu, segv, 2 * cc);
+          const int da = (cc == 0 ? ct.x : cc == 1 ? ct.y : cc == 2 ? ct.z : ct.w) >> 1;
           const float adc = cc == 0 ? adv[0] : cc == 1 ? adv[1] : cc == 2 ? adv[2] : adv[3];
           const bool single = (one_det >> cc) & 1u;
           uint32_t v[32];
@@ -399,7 +419,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
               if (col < len) { s1 += x; s2 = fmaf(x, x, s2); }
             }
           }
-          d1 += (double)s1; d2 += (double)s2;
+          f1 += s1; f2 += s2;
           if (P.segsum && rowok) {
             // GroupNorm + ReLU + per-detection sum fused into the (recomputing) second pass: the activation never
             // reaches HBM.  Run sums are fp32 in column order; runs are merged with integer atomics, so the result
@@ -464,7 +484,7 @@ gemm_tma_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const 
             }
           }
         }
-        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2(d1, d2);
+        if (p.part && rowok) p.part[((long)nt * 2 + half) * p.M + co] = make_double2((double)f1, (double)f2);
         if (P.conv && P.pool && rowok) pool_flush(co);
       }
       tc_fence_before();
@@ -616,7 +636,7 @@ static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtenso
 // g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
 static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                long rows, int ldx, int out_mode, long y_plane, cudaStream_t st,
-                               unsigned long long* segsum = nullptr, int* status = nullptr) {
+                               unsigned long long* segsum = nullptr, int* status = nullptr, const int4* chunk_tab = nullptr) {
   if (!Wp || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
   int sms = 0;
   MM_TRY(mm_sm_count(&sms));
@@ -639,6 +659,8 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   P.ksegs = 1; P.kc_per_seg = P.t.k_chunks;
   P.segsum = segsum;
   P.status = status;
+  P.chunk_tab = chunk_tab;
+  if (g.seg && (g.addend || segsum) && !chunk_tab) return MMMOT_E_ARG;
   alignas(64) CUtensorMap mh, ml;
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));

@@ -137,7 +137,7 @@ struct PnWs {
   double* stats;
   double2* part;
   int *seg, *cnt, *gstart;
-  int4* tiles;
+  int4 *tiles, *ctab;
 };
 
 // use_tc: the tensor-core path never materialises the 1024-wide activation (537 MB per frame-pair at cfg4)
@@ -167,6 +167,7 @@ PnWs carve(MmArena& a, int pairs, int L, long P, long max_tiles, bool use_tc) {
   w.seg = a.take<int>(P);
   w.cnt = a.take<int>(pairs);
   w.tiles = a.take<int4>(max_tiles);
+  w.ctab = a.take<int4>(2 * max_tiles);
   return w;
 }
 
@@ -217,6 +218,10 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   MM_LAUNCH_CHECK();
   point_segment_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(det_split, ndet, P, w.seg);
   MM_LAUNCH_CHECK();
+  if (use_tc) {
+    tma::seg_chunk_tab_kernel<<<mm_cdiv((long)tiles.size() * 2, 128), 128, 0, st>>>(w.tiles, (int)tiles.size(), w.seg, w.ctab);
+    MM_LAUNCH_CHECK();
+  }
 
   const int cin[5] = {3, 64, 64, 64, 128}, cout[5] = {64, 64, 64, 128, 1024};
   const bool timed = mm_timing_on();
@@ -274,7 +279,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
         p.Y = nullptr; p.part = nullptr;
         p.sc = w.sc; p.sh = w.sh; p.seg = w.seg;
         if (timed) mm_timing_begin(st, MM_T_PN_L5B, 2.0 * cout[i] * cin[i] * cols, 4.0 * cin[i] * cols);
-        MM_TRY(gemm_tma_launch_mat(p, wp, wps, w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st, w.segsum));
+        MM_TRY(gemm_tma_launch_mat(p, wp, wps, w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st, w.segsum, nullptr, w.ctab));
         if (timed) mm_timing_end(st);
         segsum_mean_kernel<<<mm_cdiv(1024L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 1024, ndet, w.gmean);
         MM_LAUNCH_CHECK();
@@ -299,7 +304,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       const uint4* whp = (const uint4*)wts->w[MMMOT_W_PN_WHAP];
       const float whs = wts->tc_scale[MMMOT_W_PN_WHAP];
       if (timed) mm_timing_begin(st, MM_T_PN_HEADA, 2.0 * 512 * 64 * (double)P, 4.0 * 64 * (double)P);
-      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st));
+      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, nullptr, nullptr, w.ctab));
       if (timed) mm_timing_end(st);
       MM_TRY(stats_reduce(w.part, 512, pairs, 0, w.gstart, w.stats, st, 2));
       MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1, w.sc, w.sh, st));
@@ -307,7 +312,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       MM_CUDA(cudaMemsetAsync(w.segsum, 0, (size_t)ndet * 512 * sizeof(unsigned long long), st));
       p.part = nullptr; p.sc = w.sc; p.sh = w.sh;
       if (timed) mm_timing_begin(st, MM_T_PN_HEADB, 2.0 * 512 * 64 * (double)P, 4.0 * 64 * (double)P);
-      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, w.segsum));
+      MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, w.segsum, nullptr, w.ctab));
       if (timed) mm_timing_end(st);
       segsum_mean_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 512, ndet, w.hmean);
       MM_LAUNCH_CHECK();
