@@ -106,7 +106,9 @@ enum mmmot_weight_id {
   /* ---- packed tensor-core tiles of the per-detection contractions (fusion linears, gates, w_det; BN folded) */
   MMMOT_W_FU_WPP = 221, MMMOT_W_FU_WIP = 222, MMMOT_W_FU_GATE_PP = 223, MMMOT_W_FU_GATE_IP = 224,
   MMMOT_W_WD_W1P = 225, MMMOT_W_WD_W2P = 226,
-  MMMOT_W_COUNT = 227
+  /* the two 64-output VGG layers again, compact for the pixel-major kernel: [k chunk][hi|lo][k group 4][row group 8][8][8] */
+  MMMOT_W_VGG_WPX0 = 227,         /* .. +1 */
+  MMMOT_W_COUNT = 229
 };
 
 typedef struct mmmot_weights {

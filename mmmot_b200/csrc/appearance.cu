@@ -332,7 +332,8 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
           p.S = (int)n_pix; p.tiles_per_group = mm_cdiv(n_pix, tc::BN); p.num_tiles = p.tiles_per_group;
           p.Y = reinterpret_cast<float*>(hb[which]); p.y_ms = cout;
           MM_TRY(gemm_tma_launch_mat(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0], wts->tc_scale[MMMOT_W_VGG_WP0], cols,
-                                     n_pix * 32, n_pix, 32, tma::OUT_PLANAR, plane_out, st, nullptr, status));
+                                     n_pix * 32, n_pix, 32, tma::OUT_PLANAR, plane_out, st, nullptr, status, nullptr,
+                                     (const uint4*)wts->w[MMMOT_W_VGG_WPX0]));
         }
       } else {
         GemmP p = gemm_defaults();
@@ -346,7 +347,7 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
         MM_TRY(gemm_tma_launch_conv(p, (const uint4*)wts->w[MMMOT_W_VGG_WP0 + i], wts->tc_scale[MMMOT_W_VGG_WP0 + i], cur,
                                     cur_plane, n_img, h, w, cin, hb[which], plane_out, st, kseg_scratch,
                                     kPoolAfter[i] ? plane_out / 4 : 0, &pooled_in_epilogue, status,
-                                    skip_layer ? pool_sum : nullptr));
+                                    skip_layer ? pool_sum : nullptr, i == 1 ? (const uint4*)wts->w[MMMOT_W_VGG_WPX0 + 1] : nullptr));
       }
       if (timed) mm_timing_end(st);
       cur = hb[which]; cur_plane = plane_out; which ^= 1;

@@ -48,6 +48,7 @@ struct TmaP {
   unsigned long long* segsum;   // matrix mode: if set, nothing is stored; relu(x*sc[g][co] + sh[g][co]) is summed per
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
   int* status;              // workspace status word (FP16 range flag of the planar outputs) or null
+  int wcompact;             // pixel-major kernel: t.Wp holds the compact N = 64 tiles (8 KB per k chunk, weights.py::pack_px)
   const int4* chunk_tab;    // matrix mode with g.seg: per (column tile, half) the four 32-column chunks' descriptors
                             // (first detection index << 1) | (chunk complete and inside ONE detection); see
                             // seg_chunk_tab_kernel.  One uniform 16-byte load per subtile instead of a load + 12 shuffles.
@@ -636,7 +637,8 @@ static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtenso
 // g: M, K (multiple of 32), bias, tiles, x_gs (rows per group), Y / y_ms / y_gs, part, addend...
 static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                long rows, int ldx, int out_mode, long y_plane, cudaStream_t st,
-                               unsigned long long* segsum = nullptr, int* status = nullptr, const int4* chunk_tab = nullptr) {
+                               unsigned long long* segsum = nullptr, int* status = nullptr, const int4* chunk_tab = nullptr,
+                               const uint4* Wpx = nullptr) {
   if (!Wp || g.num_tiles <= 0 || g.K % tc::BK) return MMMOT_E_ARG;
   int sms = 0;
   MM_TRY(mm_sm_count(&sms));
@@ -665,8 +667,10 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
   MM_TRY(tma::make_map_2d(&mh, Xhi, rows, g.K, ldx));
   MM_TRY(tma::make_map_2d(&ml, Xhi + x_plane, rows, g.K, ldx));
   if (out_mode == tma::OUT_PLANAR && g.M == 64 && g.y_ms == 64 && !g.part && !segsum && !g.addend && !g.tile_tab &&
-      !(P.t.dbg & 64))
+      !(P.t.dbg & 64)) {
+    if (Wpx) { P.t.Wp = Wpx; P.wcompact = 1; }
     return gemm_tma_px_launch(P, mh, ml, sms, st);
+  }
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);
@@ -682,7 +686,7 @@ static int gemm_tma_launch_mat(const GemmP& g, const uint4* Wp, float out_scale,
 static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scale, const __half* Xhi, long x_plane,
                                 int n_img, int H, int W, int C, __half* Yhi, long y_plane, cudaStream_t st,
                                 float* acc_scratch = nullptr, long y_plane_pooled = 0, int* did_pool = nullptr,
-                                int* status = nullptr, unsigned long long* pool_sum = nullptr) {
+                                int* status = nullptr, unsigned long long* pool_sum = nullptr, const uint4* Wpx = nullptr) {
   if (did_pool) *did_pool = 0;
   if (!Wp || C % tc::BK) return MMMOT_E_ARG;
   int sms = 0;
@@ -755,7 +759,10 @@ static int gemm_tma_launch_conv(const GemmP& g0, const uint4* Wp, float out_scal
   const int box_y = P.halo ? by + 2 : by;
   MM_TRY(tma::make_map_4d(&mh, Xhi, n_img, H, W, C, bx, box_y, bi));
   MM_TRY(tma::make_map_4d(&ml, Xhi + x_plane, n_img, H, W, C, bx, box_y, bi));
-  if (px) return gemm_tma_px_launch(P, mh, ml, sms, st);
+  if (px) {
+    if (Wpx) { P.t.Wp = Wpx; P.wcompact = 1; }
+    return gemm_tma_px_launch(P, mh, ml, sms, st);
+  }
   const long mgroups = (P.t.m_tiles + P.t.mt_per_cta - 1) / P.t.mt_per_cta;
   const long total = (long)g.num_tiles * mgroups;
   const int grid = (int)(total < sms ? total : sms);

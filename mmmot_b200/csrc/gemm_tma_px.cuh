@@ -210,12 +210,17 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
           const uint32_t sw = base + s * PX_STAGE, sx = sw + PX_X_OFF;
           const int kx = P.halo ? si / cchunks : 0, cc = P.halo ? si - kx * cchunks : 0;
           for (int ky = 0; ky < ntap; ky++) {
-            // rows 0..63 of the packed [hi|lo][k group 4][row group 16][8][8] tile -> compact 8 KB slot: 8 runs of 1 KB
             const int kc = P.halo ? (ky * 3 + kx) * cchunks + cc : si;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t.Wp) + (size_t)kc * P.t.m_tiles * A_SUB;
+            if (P.wcompact) {
+              // weights pre-packed for N = 64 (weights.py::pack_px): one 8 KB copy per k chunk
+              bulk_g2s(sw + ky * PX_W_SLOT, reinterpret_cast<const uint8_t*>(P.t.Wp) + (size_t)kc * PX_W_SLOT, PX_W_SLOT, full_bar(s));
+            } else {
+              // rows 0..63 of the packed [hi|lo][k group 4][row group 16][8][8] tile -> compact 8 KB slot: 8 runs of 1 KB
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(P.t.Wp) + (size_t)kc * P.t.m_tiles * A_SUB;
 #pragma unroll
-            for (int r = 0; r < 8; r++)
-              bulk_g2s(sw + ky * PX_W_SLOT + r * PX_W_LBO, src + r * A_LBO, 1024, full_bar(s));
+              for (int r = 0; r < 8; r++)
+                bulk_g2s(sw + ky * PX_W_SLOT + r * PX_W_LBO, src + r * A_LBO, 1024, full_bar(s));
+            }
           }
           if (P.halo) {
             tma_load_4d(sx, &map_hi, cc * BK, x0 + kx - 1, y0 - 1, i0, full_bar(s));

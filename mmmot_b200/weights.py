@@ -65,6 +65,16 @@ def pack_tc(wt):
     return both.view(torch.int16).reshape(-1).view(torch.uint8), 2.0 ** (-sexp)
 
 
+def pack_px(packed_u8, M, K):
+    """The compact N = 64 form of a pack_tc() result for the pixel-major kernel (64-output layers): rows 0..63 only,
+    [k chunk][hi|lo][k group 4][row group 8][8 rows][8 k] fp16 = 8 KB per k chunk, so the loader issues one bulk copy
+    per chunk instead of eight 1 KB runs out of the 128-row tile."""
+    assert M == 64
+    kc = (K + 31) // 32
+    t = packed_u8.view(torch.int16).view(kc, 1, 2, 4, 16, 8, 8)          # kc, mt, hl, kg, mg, r, e
+    return t[:, 0, :, :, :8].contiguous().reshape(-1).view(torch.uint8)
+
+
 def prepare(state_dict, fusion):
     """-> (list of fp32 CPU tensors indexed by weight id (None = unused), trans1 3x3, trans2 64x64,
     per-id tensor-core output scales)."""
@@ -186,6 +196,8 @@ def prepare(state_dict, fusion):
             else:
                 put(W["VGG_WP0"] + i, out[W["VGG_WT0"] + i])          # packed NHWC input: K order tap*Cin + ci
             i += 1
+    out[W["VGG_WPX0"]] = pack_px(out[W["VGG_WP0"]], 64, 27)
+    out[W["VGG_WPX0"] + 1] = pack_px(out[W["VGG_WP0"] + 1], 64, 576)
     for j in range(5):
         put(W["PN_WP1"] + j, out[W["PN_L1"] + 4 * j])
     put(W["PN_WHAP"], out[W["PN_WHAT"]])
