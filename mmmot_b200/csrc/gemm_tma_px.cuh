@@ -25,6 +25,14 @@ constexpr int PX_STAGE = PX_X_OFF + 2 * PX_X_PLANE;   // 72 KB
 constexpr size_t PX_SMEM_BYTES = (size_t)STAGES * PX_STAGE + 1024 + 256;
 
 constexpr uint32_t IDESC_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// Compact weight tiles (weights.py::pack_px): [k group 4][hi rows 0-63 | lo rows 0-63][8 rows][8 k], i.e. per k group a
+// 128-row K-major block whose first 64 rows are W_hi and last 64 rows W_lo.  With them the three MMAs of a k-step become
+// two:  D[:, 0:128] += X_hi * [W_hi ; W_lo]^T  (N = 128: X_hi is read from shared memory once for both products) and
+// D[:, 0:64] += X_lo * W_hi^T; the epilogue adds columns 64..127 (the X_hi*W_lo partial) to columns 0..63.  The N = 64
+// MMAs are bound by shared-memory operand bandwidth (4 KB of pixels + 2 KB of weights per 32-clock MMA = 192 B/clk
+// against 128 B/clk), so reading X_hi once per k-step instead of twice is what this buys.
+constexpr int PX_WC_LBO = 2048;
 
 static __global__ void __launch_bounds__(T_THREADS, 1)
 gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
@@ -63,7 +71,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
   }
   if (warp == T_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(256)
+                 "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -109,7 +117,16 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
           o = row * 64 + cb;
         }
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 128 + sub * 64 + cb), v);
+        if (P.wcompact) {
+          // accumulator = columns [0, 64) (hi*hi + lo*hi) + columns [64, 128) (hi*lo partial)
+          uint32_t v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + sub * 128 + cb), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + sub * 128 + 64 + cb), v2);
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 128 + sub * 64 + cb), v);
+        }
         if (P.t.dbg & 1) continue;
         if (P.pool) {
           // 2x2 max over lanes l, l^1 (x) and l^bx (y); bias + ReLU commute with the max and are applied below
@@ -179,6 +196,13 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
                 for (int ks = 0; ks < 2; ks++) {
                   const uint64_t x_hi = smem_desc_sw64(xo + sub * (128 * 64) + ks * 32);
                   const uint64_t x_lo = smem_desc_sw64(xo + PX_X_PLANE + sub * (128 * 64) + ks * 32);
+                  if (P.wcompact) {
+                    const uint64_t w_hl = smem_desc(wo + ks * 2 * PX_WC_LBO, PX_WC_LBO, SBO);   // rows 0-63 W_hi, 64-127 W_lo
+                    const uint32_t d = tmem_base + (uint32_t)(abuf * 256 + sub * 128);
+                    umma_f16(d, x_hi, w_hl, IDESC_N128, (si | ky | ks) ? 1u : 0u);
+                    umma_f16(d, x_lo, w_hl, IDESC_N64, 1u);
+                    continue;
+                  }
                   const uint64_t w_hi = smem_desc(wo + ks * 2 * PX_W_LBO, PX_W_LBO, SBO);
                   const uint64_t w_lo = smem_desc(wo + PX_W_SLOT / 2 + ks * 2 * PX_W_LBO, PX_W_LBO, SBO);
                   const uint32_t d = tmem_base + (uint32_t)(abuf * 128 + sub * 64);
@@ -243,7 +267,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
   tc_fence_before();
   __syncthreads();
   if (warp == T_MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 

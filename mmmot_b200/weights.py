@@ -67,12 +67,13 @@ def pack_tc(wt):
 
 def pack_px(packed_u8, M, K):
     """The compact N = 64 form of a pack_tc() result for the pixel-major kernel (64-output layers): rows 0..63 only,
-    [k chunk][hi|lo][k group 4][row group 8][8 rows][8 k] fp16 = 8 KB per k chunk, so the loader issues one bulk copy
-    per chunk instead of eight 1 KB runs out of the 128-row tile."""
+    [k chunk][k group 4][hi rows | lo rows][row group 8][8 rows][8 k] fp16 = 8 KB per k chunk.  One bulk copy per chunk,
+    and per k group the 64 hi rows followed by the 64 lo rows form ONE 128-row K-major operand, so X_hi * W_hi and
+    X_hi * W_lo are a single N = 128 MMA (csrc/gemm_tma_px.cuh)."""
     assert M == 64
     kc = (K + 31) // 32
     t = packed_u8.view(torch.int16).view(kc, 1, 2, 4, 16, 8, 8)          # kc, mt, hl, kg, mg, r, e
-    return t[:, 0, :, :, :8].contiguous().reshape(-1).view(torch.uint8)
+    return t[:, 0, :, :, :8].permute(0, 2, 1, 3, 4, 5).contiguous().reshape(-1).view(torch.uint8)   # kc, kg, hl, mg, r, e
 
 
 def prepare(state_dict, fusion):
