@@ -108,7 +108,9 @@ enum mmmot_weight_id {
   MMMOT_W_WD_W1P = 225, MMMOT_W_WD_W2P = 226,
   /* the two 64-output VGG layers again, compact for the pixel-major kernel: [k chunk][hi|lo][k group 4][row group 8][8][8] */
   MMMOT_W_VGG_WPX0 = 227,         /* .. +1 */
-  MMMOT_W_COUNT = 229
+  /* packed tiles of the remaining small contractions: new/end MLP, PointNet per-detection parts */
+  MMMOT_W_NE_W1P = 229, MMMOT_W_NE_W2P = 230, MMMOT_W_PN_WHGP = 231, MMMOT_W_PN_WOP = 232,
+  MMMOT_W_COUNT = 233
 };
 
 typedef struct mmmot_weights {

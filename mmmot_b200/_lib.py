@@ -32,7 +32,7 @@ W = dict(
     NE_W3=137, NE_B3=138,
     VGG_WP0=139, PN_WP1=152, PN_WHAP=157, AF_W01P=158, AF_W2P=159, AF_W3P=160,
     VGG_RAWW0=161, VGG_RAWB0=174, VGG_BNW0=187, VGG_BNB0=200, WD_RAW0=213,
-    FU_WPP=221, FU_WIP=222, FU_GATE_PP=223, FU_GATE_IP=224, WD_W1P=225, WD_W2P=226, VGG_WPX0=227, COUNT=229,
+    FU_WPP=221, FU_WIP=222, FU_GATE_PP=223, FU_GATE_IP=224, WD_W1P=225, WD_W2P=226, VGG_WPX0=227, NE_W1P=229, NE_W2P=230, PN_WHGP=231, PN_WOP=232, COUNT=233,
 )
 
 

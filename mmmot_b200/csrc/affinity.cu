@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) rowcol_mean_kernel(const float* __restric
 __global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __restrict__ y, long ld, int coff,
                                                              const float* __restrict__ sc, const float* __restrict__ sh,
                                                              int N, int M, long ldv, float* __restrict__ V, int mx) {
+  // ldv == 0: V is channels-last [column][512] (the tensor-core new/end MLP reads it as rows); else V[c][ldv]
   const int g = blockIdx.x / (N + M), r = blockIdx.x % (N + M);
   const bool is_end = r < N;
   const int cnt = is_end ? M : N;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(256) newend_mean_cl_kernel(const float* __rest
       const float r2 = fmaxf(fmaf(__ldg(p + (long)k * step), a, b), 0.f);
       acc = mx ? fmaxf(acc, r2) : acc + r2;
     }
-    V[(long)c * ldv + (long)g * (M + N) + (is_end ? M + r : r - N)] = mx ? acc : acc / (float)cnt;
+    const long colv = (long)g * (M + N) + (is_end ? M + r : r - N);
+    V[ldv ? (long)c * ldv + colv : colv * 512 + c] = mx ? acc : acc / (float)cnt;
   }
 }
 // z[row] = w4 . relu(GN(y3[row][0..127])) + b4 : one warp per row (a lane owns 4 channels: one coalesced 512-byte
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256) link_logit_cl_kernel(const float* __restr
 }
 
 // Tile table for the new/end MLP: group 2g = new columns (len M), 2g+1 = end columns (len N).
-__global__ void ne_tiles_kernel(int G, int N, int M, int tn, int tm_, int4* __restrict__ tiles,
+__global__ void ne_tiles_kernel(int G, int N, int M, int tn, int tm_, int tw, int4* __restrict__ tiles,
                                 int* __restrict__ cnt, int* __restrict__ gstart) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int per = tm_ + tn;  // tiles per g: tm_ for the M new columns, tn for the N end columns
@@ -142,8 +144,8 @@ __global__ void ne_tiles_kernel(int G, int N, int M, int tn, int tm_, int4* __re
   if (idx == G * 2) gstart[idx] = G * per;
   if (idx >= G * per) return;
   int g = idx / per, t = idx - g * per;
-  if (t < tm_) tiles[idx] = make_int4(2 * g, g * (M + N) + t * 128, min(128, M - t * 128), 0);
-  else { t -= tm_; tiles[idx] = make_int4(2 * g + 1, g * (M + N) + M + t * 128, min(128, N - t * 128), 0); }
+  if (t < tm_) tiles[idx] = make_int4(2 * g, g * (M + N) + t * tw, min(tw, M - t * tw), 0);
+  else { t -= tm_; tiles[idx] = make_int4(2 * g + 1, g * (M + N) + M + t * tw, min(tw, N - t * tw), 0); }
 }
 
 // out[col] = sigmoid(w3 . relu(GN(h2))[:, col] + b3) for the new/end MLP; scatters into new_s / end_s.
@@ -160,6 +162,29 @@ __global__ void ne_final_kernel(const float* __restrict__ h2, long ldv, const fl
     a = fmaf(w3[c], fmaxf(fmaf(h2[(long)c * ldv + idx], sc[grp * 128 + c], sh[grp * 128 + c]), 0.f), a);
   float s = mm_sigmoid(a);
   if (r < M) new_s[(long)g * M + r] = s; else end_s[(long)g * N + (r - M)] = s;
+}
+
+// channels-last variant: h2[col][128]; one warp per column (a lane owns 4 channels)
+__global__ void ne_final_cl_kernel(const float* __restrict__ h2, const float* __restrict__ sc, const float* __restrict__ sh,
+                                   const float* __restrict__ w3, const float* __restrict__ b3, int G, int N, int M,
+                                   float* __restrict__ new_s, float* __restrict__ end_s) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= G * (M + N)) return;
+  const int g = idx / (M + N), r = idx - g * (M + N);
+  const int grp = 2 * g + (r >= M);
+  const float4 x = *reinterpret_cast<const float4*>(h2 + (long)idx * 128 + lane * 4);
+  const float4 a = *reinterpret_cast<const float4*>(sc + grp * 128 + lane * 4), b = *reinterpret_cast<const float4*>(sh + grp * 128 + lane * 4);
+  const float4 w = *reinterpret_cast<const float4*>(w3 + lane * 4);
+  float acc = w.x * fmaxf(fmaf(x.x, a.x, b.x), 0.f);
+  acc = fmaf(w.y, fmaxf(fmaf(x.y, a.y, b.y), 0.f), acc);
+  acc = fmaf(w.z, fmaxf(fmaf(x.z, a.z, b.z), 0.f), acc);
+  acc = fmaf(w.w, fmaxf(fmaf(x.w, a.w, b.w), 0.f), acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float sv = mm_sigmoid(acc + b3[0]);
+    if (r < M) new_s[(long)g * M + r] = sv; else end_s[(long)g * N + (r - M)] = sv;
+  }
 }
 
 // z[g][s] = w4 . relu(GN(y3[g]))[:, s] + b4      (reference gcn.py:65-66: last 1x1 conv 128 -> 1)
@@ -260,7 +285,7 @@ AfWs carve(MmArena& a, int pairs, int n, int m) {
   w.cnt = a.take<int>(2 * G);
   w.gstart = a.take<int>(2 * G + 1);
   w.part = a.take<double2>(G * 2 * mm_cdiv(NM, 256) * 1024);   // covers 1 partial per 128-tile and 2 per 256-tile
-  w.npart = a.take<double2>(G * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);
+  w.npart = a.take<double2>(G * 2 * (mm_cdiv(n, 128) + mm_cdiv(m, 128)) * 512);   // 1 partial per 128-tile or 2 per 256-tile
   return w;
 }
 
@@ -339,7 +364,7 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   const long ldv = (long)G * (n + m);
   if (use_tc) {
     if (timed) mm_timing_begin(st, MM_T_AFF_MEAN, 0.0, 4.0 * 512 * (double)G * NM);
-    newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, ldv, w.v, end_mode);
+    newend_mean_cl_kernel<<<G * (n + m), 256, 0, st>>>(w.y01, 1024, 512, w.sc0, w.sh0, n, m, 0, w.v, end_mode);
     MM_LAUNCH_CHECK();
     if (timed) mm_timing_end(st);
   } else {
@@ -347,10 +372,30 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
                                                                n, m, ldv, w.v, end_mode);
     MM_LAUNCH_CHECK();
   }
-  const int tn = mm_cdiv(n, 128), tm_ = mm_cdiv(m, 128), ne_tiles = G * (tn + tm_);
-  ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G + 1), 128), 128, 0, st>>>(G, n, m, tn, tm_, w.tiles, w.cnt, w.gstart);
+  const int tw = use_tc ? tc::BN : 128;
+  const int tn = mm_cdiv(n, tw), tm_ = mm_cdiv(m, tw), ne_tiles = G * (tn + tm_);
+  ne_tiles_kernel<<<mm_cdiv(max(ne_tiles, 2 * G + 1), 128), 128, 0, st>>>(G, n, m, tn, tm_, tw, w.tiles, w.cnt, w.gstart);
   MM_LAUNCH_CHECK();
-  {
+  if (use_tc) {
+    // shared Conv1d MLP on the new / end vectors (new_end.py:53-60) on the tensor cores: rows = columns of V
+    // (channels-last), groups = (g, new | end) through the tile table
+    GemmP p = gemm_defaults();
+    p.bias = W[MMMOT_W_NE_B1]; p.M = 512; p.K = 512;
+    p.tile_tab = w.tiles; p.num_tiles = ne_tiles;
+    p.Y = w.h1; p.y_ms = 512;
+    p.part = w.npart;
+    MM_TRY(launch_gen<gen::GEN_COPY>(p, wts, MMMOT_W_NE_W1P, w.v, 512, nullptr, nullptr, 0, 0, 0, st));
+    MM_TRY(stats_reduce(w.npart, 512, 2 * G, 0, w.gstart, w.nstats, st, 2));
+    MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G1W], W[MMMOT_W_NE_G1B], w.cnt, 0, 2 * G, 512, 512, w.nsc1, w.nsh1, st, 0, 0, ar.status()));
+    p.bias = W[MMMOT_W_NE_B2]; p.M = 128;
+    p.Y = w.h2; p.y_ms = 128;
+    MM_TRY(launch_gen<gen::GEN_NORM>(p, wts, MMMOT_W_NE_W2P, w.h1, 512, w.nsc1, w.nsh1, 0, 0, 0, st));
+    MM_TRY(stats_reduce(w.npart, 128, 2 * G, 0, w.gstart, w.nstats, st, 2));
+    MM_TRY(gn_finalize(w.nstats, W[MMMOT_W_NE_G2W], W[MMMOT_W_NE_G2B], w.cnt, 0, 2 * G, 128, 128, w.nsc2, w.nsh2, st));
+    ne_final_cl_kernel<<<mm_cdiv((long)G * (n + m) * 32, 256), 256, 0, st>>>(w.h2, w.nsc2, w.nsh2, W[MMMOT_W_NE_W3], W[MMMOT_W_NE_B3],
+                                                                            G, n, m, new_s, end_s);
+    MM_LAUNCH_CHECK();
+  } else {
     GemmP p = gemm_defaults();
     p.Wt = W[MMMOT_W_NE_W1T]; p.bias = W[MMMOT_W_NE_B1]; p.ldw = 512; p.M = 512; p.K = 512;
     p.tile_tab = w.tiles; p.num_tiles = ne_tiles;

@@ -354,7 +354,9 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
       if (kPoolAfter[i]) {
         h /= 2; w /= 2;
         const long plane_p = (long)n_img * h * w * cout;
-        if (timed) mm_timing_begin(st, MM_T_VGG_POOL, 0.0, pooled_in_epilogue ? 4.0 * plane_p : 4.0 * 5.0 * plane_p);
+        // compulsory bytes: separate pool = read the map + write the pooled one (+ read it again for the mean); fused =
+        // the per-image sums only
+        if (timed) mm_timing_begin(st, MM_T_VGG_POOL, 0.0, pooled_in_epilogue ? 12.0 * n_img * cout : 4.0 * 6.0 * plane_p);
         if (pooled_in_epilogue) {
           cur_plane = plane_p;
         } else {

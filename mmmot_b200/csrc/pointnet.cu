@@ -129,6 +129,31 @@ __global__ void segsum_mean_kernel(const unsigned long long* __restrict__ segsum
   out[(long)c * ndet + d] = cnt > 0 ? (float)((double)segsum[idx] * (1.0 / 4294967296.0) / (double)cnt) : 0.f;
 }
 
+// channels-last variant: out[d][C] (the layout the tensor-core per-detection contractions read as rows)
+__global__ void segsum_mean_cl_kernel(const unsigned long long* __restrict__ segsum, const int* __restrict__ split,
+                                      int C, int ndet, float* __restrict__ out) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)C * ndet) return;
+  const int d = (int)(idx / C);
+  const int cnt = split[d + 1] - split[d];
+  out[idx] = cnt > 0 ? (float)((double)segsum[idx] * (1.0 / 4294967296.0) / (double)cnt) : 0.f;
+}
+// feats[pair][1][c][l] = relu(O[d][c]*sc[pair][c] + sh[pair][c]) from channels-last O (32 x 32 tiles through smem)
+__global__ void pointnet_out_cl_kernel(const float* __restrict__ O, const float* __restrict__ sc, const float* __restrict__ sh,
+                                       int L, float* __restrict__ feats) {
+  __shared__ float tile[32][33];
+  const int pair = blockIdx.z, c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int l = l0 + i, c = c0 + threadIdx.x;
+    if (l < L) tile[i][threadIdx.x] = fmaxf(fmaf(O[((long)pair * L + l) * 512 + c], sc[pair * 512 + c], sh[pair * 512 + c]), 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, l = l0 + threadIdx.x;
+    if (l < L) feats[(((long)pair * 3 + 1) * 512 + c) * L + l] = tile[threadIdx.x][i];
+  }
+}
+
 struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *ut, *hmean, *o;
   unsigned long long* segsum;   // tensor-core path: [ndet][1024] fixed-point per-detection sums
@@ -281,18 +306,20 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
         if (timed) mm_timing_begin(st, MM_T_PN_L5B, 2.0 * cout[i] * cin[i] * cols, 4.0 * cin[i] * cols);
         MM_TRY(gemm_tma_launch_mat(p, wp, wps, w.xp, P * cin[i], P, cin[i], tc::OUT_CL, 0, st, w.segsum, nullptr, w.ctab));
         if (timed) mm_timing_end(st);
-        segsum_mean_kernel<<<mm_cdiv(1024L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 1024, ndet, w.gmean);
+        segsum_mean_cl_kernel<<<mm_cdiv(1024L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 1024, ndet, w.gmean);
         MM_LAUNCH_CHECK();
       }
     }
     {
+      // U[det][512] = gmean[det][1024] Wh[:, 64:]^T  (the per-detection part of point_net.py:27-28's conv1), on the
+      // tensor cores over channels-last rows; its output is directly the [det][512] addend table of the head
       GemmP p = gemm_defaults();
-      p.Wt = wts->w[MMMOT_W_PN_WHGT]; p.ldw = 512; p.M = 512; p.K = 1024;
-      p.S = ndet; p.tiles_per_group = mm_cdiv(ndet, 128); p.num_tiles = p.tiles_per_group;
-      p.X = w.gmean; p.x_ks = ndet;
-      p.Y = w.u; p.y_ms = ndet;
-      MM_TRY(gemm_simt_launch<XM_DIRECT>(p, st));
-      MM_TRY(transpose_f32(w.u, w.ut, 512, ndet, 1, st));     // -> [det][512] for coalesced epilogue reads
+      p.M = 512; p.K = 1024;
+      p.S = ndet; p.tiles_per_group = mm_cdiv(ndet, tc::BN); p.num_tiles = p.tiles_per_group;
+      p.x_gs = ndet;
+      p.Y = w.ut; p.y_gs = ndet; p.y_ms = 512;
+      MM_TRY((gemm_gen_launch<gen::GEN_COPY>(p, (const uint4*)wts->w[MMMOT_W_PN_WHGP], wts->tc_scale[MMMOT_W_PN_WHGP], w.gmean, 1024,
+                                             nullptr, nullptr, 0, 0, 0, st)));
     }
     {
       GemmP p = gemm_defaults();
@@ -314,8 +341,25 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       if (timed) mm_timing_begin(st, MM_T_PN_HEADB, 2.0 * 512 * 64 * (double)P, 4.0 * 64 * (double)P);
       MM_TRY(gemm_tma_launch_mat(p, whp, whs, w.x1p, P * 64, P, 64, tc::OUT_CL, 0, st, w.segsum, nullptr, w.ctab));
       if (timed) mm_timing_end(st);
-      segsum_mean_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 512, ndet, w.hmean);
+      segsum_mean_cl_kernel<<<mm_cdiv(512L * ndet, 256), 256, 0, st>>>(w.segsum, det_split, 512, ndet, w.hmean);
       MM_LAUNCH_CHECK();
+    }
+    {
+      // conv2 512 -> 512 over the pair's L detections, GroupNorm(16,512), ReLU (point_net.py:40-41), on the tensor cores
+      const int tpg2 = mm_cdiv(L, tc::BN);
+      GemmP p = gemm_defaults();
+      p.bias = wts->w[MMMOT_W_PN_BO]; p.M = 512; p.K = 512;
+      p.S = L; p.tiles_per_group = tpg2; p.num_tiles = tpg2 * pairs;
+      p.x_gs = L;
+      p.Y = w.o; p.y_gs = L; p.y_ms = 512;
+      p.part = w.part;
+      MM_TRY((gemm_gen_launch<gen::GEN_COPY>(p, (const uint4*)wts->w[MMMOT_W_PN_WOP], wts->tc_scale[MMMOT_W_PN_WOP], w.hmean, 512,
+                                             nullptr, nullptr, 0, 0, 0, st)));
+      MM_TRY(stats_reduce(w.part, 512, pairs, tpg2, nullptr, w.stats, st, 2));
+      MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GOW], wts->w[MMMOT_W_PN_GOB], nullptr, L, pairs, 512, 32, w.sc, w.sh, st));
+      pointnet_out_cl_kernel<<<dim3(mm_cdiv(L, 32), 16, pairs), dim3(32, 8), 0, st>>>(w.o, w.sc, w.sh, L, feats);
+      MM_LAUNCH_CHECK();
+      return 0;
     }
   } else {
   // trunk: 3 -> 64 -> 64 -> 64 -> 128 -> 1024, each conv + GroupNorm(C,C) over the pair's points + ReLU

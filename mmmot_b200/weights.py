@@ -206,7 +206,8 @@ def prepare(state_dict, fusion):
     put(W["AF_W2P"], out[W["AF_W2T"]])
     put(W["AF_W3P"], out[W["AF_W3T"]])
     for wid, src in (("FU_WPP", "FU_WPT"), ("FU_WIP", "FU_WIT"), ("FU_GATE_PP", "FU_GATE_PT"), ("FU_GATE_IP", "FU_GATE_IT"),
-                     ("WD_W1P", "WD_W1T"), ("WD_W2P", "WD_W2T")):
+                     ("WD_W1P", "WD_W1T"), ("WD_W2P", "WD_W2T"), ("NE_W1P", "NE_W1T"), ("NE_W2P", "NE_W2T"),
+                     ("PN_WHGP", "PN_WHGT"), ("PN_WOP", "PN_WOT")):
         if out[W[src]] is not None:
             put(W[wid], out[W[src]])
     out = [t.view(torch.float32) if (t is not None and t.dtype == torch.uint8) else t for t in out]
