@@ -127,6 +127,12 @@ int mmmot_abi_version(void);
  * as FP16 hi/lo pairs; a value with |x| >= 65504 saturates in that conversion, which these calls make loud. */
 int mmmot_status_reset(void* workspace, void* stream);
 int mmmot_status_check(const void* workspace, void* stream);
+/* Small stream-ordered host -> device transfer that uses NEITHER the copy engine NOR a host synchronisation: a kernel
+ * reads `count` int32 words straight from PINNED (page-locked, mapped) host memory.  For the CSR offsets that accompany
+ * a sub-batch: a cudaMemcpyAsync of them would queue on the copy engine behind the bulk input copies of the NEXT
+ * sub-batch (stalling the compute stream for milliseconds), a pageable copy blocks the calling thread.  The source
+ * must stay untouched until the stream has passed this call.  MMMOT_E_ARG if `src_pinned_host` is not pinned. */
+int mmmot_fetch_pinned_i32(int* dst_device, const int* src_pinned_host, long count, void* stream);
 /* number of SMs / name of the current device: lets the host fail loudly when no sm_100 GPU is present */
 int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

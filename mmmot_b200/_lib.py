@@ -64,6 +64,7 @@ SIGNATURES = {
     "mmmot_timing_collect_tags": (_i, [ctypes.POINTER(ctypes.c_double)] * 3 + [ctypes.POINTER(ctypes.c_long)]),
     "mmmot_status_reset": (_i, [_vp, _vp]),
     "mmmot_status_check": (_i, [_vp, _vp]),
+    "mmmot_fetch_pinned_i32": (_i, [_vp, _vp, _l, _vp]),
     "mmmot_debug_linear_gen": (_i, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mmmot_timing_collect": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),

@@ -1,4 +1,5 @@
 // Library-wide entry points of libmmmot_sm100a.so (see include/mmmot_b200.h).
+#include <algorithm>
 #include <atomic>
 
 #include "common.cuh"
@@ -37,6 +38,25 @@ extern "C" int mmmot_status_check(const void* workspace, void* stream) {
   MM_CUDA(cudaMemcpyAsync(&word, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return (word & 1) ? MMMOT_E_RANGE : 0;
+}
+
+// ---- pinned-host fetch (see header): zero-copy read over PCIe by a kernel, stream-ordered ----
+__global__ void fetch_pinned_i32_kernel(int* __restrict__ dst, const int* __restrict__ src, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+extern "C" int mmmot_fetch_pinned_i32(int* dst_device, const int* src_pinned_host, long count, void* stream) {
+  if (!dst_device || !src_pinned_host || count < 0) return MMMOT_E_ARG;
+  if (count == 0) return 0;
+  void* dsrc = nullptr;
+  if (cudaHostGetDevicePointer(&dsrc, const_cast<int*>(src_pinned_host), 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return MMMOT_E_ARG;
+  }
+  const int blocks = (int)std::min<long>(mm_cdiv(count, 256), 32);
+  fetch_pinned_i32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dst_device, (const int*)dsrc, count);
+  MM_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int mmmot_device_info(int* sm_count, int* cc_major, int* cc_minor) {

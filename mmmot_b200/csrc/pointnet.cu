@@ -154,6 +154,30 @@ __global__ void pointnet_out_cl_kernel(const float* __restrict__ O, const float*
   }
 }
 
+// Column-tile table of the ragged per-pair point ranges, built ON THE DEVICE from the CSR offsets (the host only
+// needs the tile count for its launch geometry): no pageable host->device copy, so the calling thread never blocks on
+// the stream and can keep enqueueing.  gstart[p] = first tile of pair p (one thread: pairs is small), then one thread
+// per pair fills its tiles {pair, first point, length <= tw}.
+__global__ void pn_tiles_kernel(const int* __restrict__ split, int pairs, int L, int tw, int* __restrict__ cnt,
+                                int* __restrict__ gstart, int4* __restrict__ tiles) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int p = 0; p < pairs; p++) {
+      const int n = split[(p + 1) * L] - split[p * L];
+      cnt[p] = n;
+      gstart[p] = acc;
+      acc += (n + tw - 1) / tw;
+    }
+    gstart[pairs] = acc;
+  }
+  __syncthreads();   // single CTA: the prefix is visible to all its threads
+  for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+    const int s0 = split[p * L], e = split[(p + 1) * L];
+    int t = gstart[p];
+    for (int c = s0; c < e; c += tw) tiles[t++] = make_int4(p, c, min(tw, e - c), 0);
+  }
+}
+
 struct PnWs {
   float *xt, *y1, *t0, *t1, *big, *gmean, *u, *ut, *hmean, *o;
   unsigned long long* segsum;   // tensor-core path: [ndet][1024] fixed-point per-detection sums
@@ -222,29 +246,21 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
   const bool use_tc = pointnet_use_tc(L);
   const int TNW = use_tc ? tc::BN : 128;
-  std::vector<int4> tiles;
-  std::vector<int> cnt(pairs), gstart(pairs + 1);
-  for (int p = 0; p < pairs; p++) {
-    int s = h_det_split[p * L], e = h_det_split[(p + 1) * L];
-    cnt[p] = e - s;
-    gstart[p] = (int)tiles.size();
-    for (int c = s; c < e; c += TNW) tiles.push_back(make_int4(p, c, min(TNW, e - c), 0));
-  }
-  gstart[pairs] = (int)tiles.size();
+  long n_tiles = 0;   // the host needs only the COUNT (launch geometry); the table itself is built on the device
+  for (int p = 0; p < pairs; p++) n_tiles += mm_cdiv((long)h_det_split[(p + 1) * L] - h_det_split[p * L], TNW);
   const long max_tiles = P / 128 + 2 * pairs + 2;   // also bounds 2 partials per 256-wide tile
   MmArena ar(workspace, workspace_bytes);
   PnWs w = carve(ar, pairs, L, P, max_tiles, use_tc);
-  if (!ar.ok() || (long)tiles.size() > max_tiles) return MMMOT_E_WORKSPACE;
-  MM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-  MM_CUDA(cudaMemcpyAsync(w.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  MM_CUDA(cudaMemcpyAsync(w.gstart, gstart.data(), gstart.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!ar.ok() || n_tiles > max_tiles) return MMMOT_E_WORKSPACE;
+  pn_tiles_kernel<<<1, 256, 0, st>>>(det_split, pairs, L, TNW, w.cnt, w.gstart, w.tiles);
+  MM_LAUNCH_CHECK();
 
   transpose_points_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(points, w.xt, P);
   MM_LAUNCH_CHECK();
   point_segment_kernel<<<mm_cdiv(P, 256), 256, 0, st>>>(det_split, ndet, P, w.seg);
   MM_LAUNCH_CHECK();
   if (use_tc) {
-    tma::seg_chunk_tab_kernel<<<mm_cdiv((long)tiles.size() * 2, 128), 128, 0, st>>>(w.tiles, (int)tiles.size(), w.seg, w.ctab);
+    tma::seg_chunk_tab_kernel<<<mm_cdiv(n_tiles * 2, 128), 128, 0, st>>>(w.tiles, (int)n_tiles, w.seg, w.ctab);
     MM_LAUNCH_CHECK();
   }
 
@@ -260,7 +276,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
       GemmP p = gemm_defaults();
       p.bias = q[1]; p.M = cout[i]; p.K = cin[i];
-      p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+      p.tile_tab = w.tiles; p.num_tiles = (int)n_tiles;
       p.Y = ybuf[i]; p.y_ms = cout[i];       // layer 5 (1024 wide): statistics only, nothing stored
       p.part = w.part;
       const uint4* wp = (const uint4*)wts->w[MMMOT_W_PN_WP1 + i];
@@ -268,7 +284,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
       const double cols = (double)P;
       if (i == 0) {
         if (timed) mm_timing_begin(st, MM_T_PN_L1, 2.0 * 64 * 3 * cols, 12.0 * cols);
-        pn_l1_stats_kernel<<<(int)tiles.size(), 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
+        pn_l1_stats_kernel<<<(int)n_tiles, 256, 0, st>>>(points, w.tiles, q[0], q[1], w.part);
         MM_LAUNCH_CHECK();
         if (timed) mm_timing_end(st);
       } else {
@@ -324,7 +340,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     {
       GemmP p = gemm_defaults();
       p.bias = wts->w[MMMOT_W_PN_BH]; p.M = 512; p.K = 64;
-      p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+      p.tile_tab = w.tiles; p.num_tiles = (int)n_tiles;
       p.Y = nullptr; p.y_ms = 512;           // pass 1: statistics only
       p.part = w.part;
       p.addend = w.ut; p.seg = w.seg; p.ld_add = 512;
@@ -369,7 +385,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     const float* const* q = &wts->w[MMMOT_W_PN_L1 + 4 * i];
     GemmP p = gemm_defaults();
     p.Wt = q[0]; p.bias = q[1]; p.ldw = cout[i]; p.M = cout[i]; p.K = cin[i];
-    p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+    p.tile_tab = w.tiles; p.num_tiles = (int)n_tiles;
     p.X = src[i]; p.x_ks = P;
     p.Y = dst[i]; p.y_ms = P;
     p.part = w.part;
@@ -401,7 +417,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
   {
     GemmP p = gemm_defaults();
     p.Wt = wts->w[MMMOT_W_PN_WHAT]; p.bias = wts->w[MMMOT_W_PN_BH]; p.ldw = 512; p.M = 512; p.K = 64;
-    p.tile_tab = w.tiles; p.num_tiles = (int)tiles.size();
+    p.tile_tab = w.tiles; p.num_tiles = (int)n_tiles;
     p.X = w.y1; p.x_ks = P; p.sc = w.sc1; p.sh = w.sh1;
     p.Y = w.big; p.y_ms = P;
     p.part = w.part;

@@ -121,6 +121,31 @@ class TrackingNet(nn.Module):
             self._prepared = DeviceWeights(self.state_dict(), self.score_fusion_arch, dev)
         return self._prepared
 
+    def _split_to_device(self, s_host, dev):
+        """CSR offsets host -> device without blocking the calling thread and without the copy engine: staged in a small
+        ring of pinned buffers that a kernel reads over PCIe (mmmot_fetch_pinned_i32).  A pageable copy would make the
+        host wait for everything already enqueued on the stream; a cudaMemcpyAsync from pinned memory queues on the
+        copy engine behind the bulk input copies of a pipelined caller (HostPipeline) and stalls the compute stream for
+        milliseconds per sub-batch (measured: 7 % of cfg4's e2e).  A slot is reused only after its fetch has executed."""
+        n = s_host.numel()
+        ring = getattr(self, "_pin_ring", None)
+        if ring is None or ring[0][0].numel() < n:
+            cap = max(n, 1024)
+            ring = self._pin_ring = [[torch.empty(cap, dtype=torch.int32, pin_memory=True), None] for _ in range(4)]
+            self._pin_next = 0
+        slot = ring[self._pin_next]
+        self._pin_next = (self._pin_next + 1) % len(ring)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0][:n].copy_(s_host)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        _lib.check(_lib.load().mmmot_fetch_pinned_i32(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(slot[0].data_ptr()), n,
+                                                      ctypes.c_void_p(cur.cuda_stream)), "mmmot_fetch_pinned_i32")
+        slot[1] = torch.cuda.Event()
+        slot[1].record(cur)
+        return out
+
     def _workspace(self, nbytes, dev):
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
             self._ws = None
@@ -231,7 +256,7 @@ class TrackingNet(nn.Module):
                 s_host = split[p0 * L:(p0 + pc) * L + 1]
                 off = int(s_host[0])
                 s_host = (s_host - off).contiguous()
-                s_dev = s_host.to(dev, non_blocking=False)
+                s_dev = self._split_to_device(s_host, dev)
                 self._run_chunk(lib, wts, crops[p0 * L:(p0 + pc) * L], points[off:off + int(s_host[-1])],
                                 s_dev, s_host, pc, n, m, out, p0)
         out["trans"] = [wts.trans1.unsqueeze(0).clone(), wts.trans2.unsqueeze(0).clone()]

@@ -97,6 +97,24 @@ def test_fp16_range_is_reported_not_clamped():
         mmmot_b200.set_engine("auto")
 
 
+def test_fetch_pinned_i32():
+    """mmmot_fetch_pinned_i32: stream-ordered host -> device transfer of the CSR offsets by a kernel reading pinned host
+    memory (no copy engine, no host synchronisation); pageable memory is refused loudly."""
+    import ctypes
+    from mmmot_b200 import _lib
+    lib = _lib.load()
+    for n in (1, 257, 8193, 100001):
+        src = torch.empty(n, dtype=torch.int32, pin_memory=True).copy_(torch.arange(n, dtype=torch.int32) * 3 - 7)
+        dst = torch.full((n + 1,), -1, dtype=torch.int32, device="cuda")
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert lib.mmmot_fetch_pinned_i32(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()), n, st) == 0
+        assert torch.equal(dst[:n].cpu(), src) and int(dst[n]) == -1
+    pageable = torch.arange(16, dtype=torch.int32)
+    dst = torch.zeros(16, dtype=torch.int32, device="cuda")
+    assert lib.mmmot_fetch_pinned_i32(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(pageable.data_ptr()), 16, None) == -1
+    torch.cuda.synchronize()
+
+
 def test_score_arch_branch_reg_has_no_sigmoid():
     """reference tracking_net.py:153-156: the sigmoid is applied only when 'cls' is in score_arch."""
     dets, info, split = synthetic_pair(6, 6, 24, 32, seed=2)
