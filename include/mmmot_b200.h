@@ -183,12 +183,23 @@ int mmmot_fusion_det_fwd(const mmmot_weights* wts, int fusion_arch, int score_fl
  *   mmmot_appearance_train_fwd: as mmmot_appearance_fwd; bn_stats [13][2][512] = per layer (batch mean | biased batch
  *     variance) per channel, for the caller's running-average update.
  *   mmmot_w_det_train_fwd: feats [3][512][L] of one pair -> det_scores [3][L] raw logits; bn_stats [2][2][512].
- * The other stages (PointNet, fusion, affinity) have no BatchNorm: the eval entry points serve both modes
+ *     drop_mask2 / drop_mask3 (NULL = none): DropBlock2D weights of the two deepest SkipPool heads
+ *     (modules/appear_net.py:27-30,143-152; modules/dropblock.py:28-55), [n_img][H/16][W/16] and [n_img][H/32][W/32] =
+ *     block_mask * numel / sum.  The caller draws the Bernoulli seeds (the reference draws them with torch's CPU generator,
+ *     which a bit-matching run has to share) and max-pools them into blocks; the library applies them before the mean.
+ *   mmmot_pointnet_train_fwd: as mmmot_pointnet_fwd on the FP32 engine, with the optional nn.Dropout mask of the head
+ *     activation (modules/point_net.py:29-30): head_drop_mask [512][P], values {0, 1/(1-p)}, NULL = none.
+ * Fusion and affinity have neither BatchNorm nor dropout: the eval entry points serve both modes
  * (mmmot_fusion_det_fwd's det_scores are simply overwritten by mmmot_w_det_train_fwd's).  Forward only: no gradients.
  */
 size_t mmmot_appearance_train_workspace(int n_img, int H, int W);
 int mmmot_appearance_train_fwd(const mmmot_weights* wts, const float* crops, int n_img, int H, int W, int L,
-                               float* feats, float* bn_stats, void* workspace, size_t workspace_bytes, void* stream);
+                               float* feats, float* bn_stats, const float* drop_mask2, const float* drop_mask3,
+                               void* workspace, size_t workspace_bytes, void* stream);
+size_t mmmot_pointnet_train_workspace(int pairs, int L, long p_total);
+int mmmot_pointnet_train_fwd(const mmmot_weights* wts, const float* points, const int* det_split, const int* h_det_split,
+                             int pairs, int L, const float* head_drop_mask, float* feats, void* workspace,
+                             size_t workspace_bytes, void* stream);
 size_t mmmot_w_det_train_workspace(int L);
 int mmmot_w_det_train_fwd(const mmmot_weights* wts, int L, const float* feats, float* det_scores, float* bn_stats,
                           void* workspace, size_t workspace_bytes, void* stream);

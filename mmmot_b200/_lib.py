@@ -70,7 +70,9 @@ SIGNATURES = {
     "mmmot_appearance_workspace": (_sz, [_i, _i, _i]),
     "mmmot_appearance_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmmot_appearance_train_workspace": (_sz, [_i, _i, _i]),
-    "mmmot_appearance_train_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_appearance_train_fwd": (_i, [_wp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mmmot_pointnet_train_workspace": (_sz, [_i, _i, _l]),
+    "mmmot_pointnet_train_fwd": (_i, [_wp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_w_det_train_workspace": (_sz, [_i]),
     "mmmot_w_det_train_fwd": (_i, [_wp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mmmot_pointnet_workspace": (_sz, [_i, _i, _l]),

@@ -48,11 +48,12 @@ __global__ void fetch_pinned_i32_kernel(int* __restrict__ dst, const int* __rest
 extern "C" int mmmot_fetch_pinned_i32(int* dst_device, const int* src_pinned_host, long count, void* stream) {
   if (!dst_device || !src_pinned_host || count < 0) return MMMOT_E_ARG;
   if (count == 0) return 0;
-  void* dsrc = nullptr;
-  if (cudaHostGetDevicePointer(&dsrc, const_cast<int*>(src_pinned_host), 0) != cudaSuccess) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, src_pinned_host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
     (void)cudaGetLastError();
-    return MMMOT_E_ARG;
+    return MMMOT_E_ARG;     // pageable (unregistered) or device memory
   }
+  const void* dsrc = at.devicePointer;
   const int blocks = (int)std::min<long>(mm_cdiv(count, 256), 32);
   fetch_pinned_i32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dst_device, (const int*)dsrc, count);
   MM_LAUNCH_CHECK();

@@ -91,7 +91,7 @@ __global__ void point_segment_kernel(const int* __restrict__ split, int ndet, lo
 // One warp per (c, d); lanes stride the segment (coalesced).
 __global__ void segment_mean_kernel(const float* __restrict__ Y, long P, const int* __restrict__ split,
                                     const float* __restrict__ sc, const float* __restrict__ sh, int C,
-                                    int ndet, int L, float* __restrict__ out) {
+                                    int ndet, int L, float* __restrict__ out, const float* __restrict__ mask = nullptr) {
   long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= (long)C * ndet) return;
@@ -101,7 +101,12 @@ __global__ void segment_mean_kernel(const float* __restrict__ Y, long P, const i
   int s = split[d], e = split[d + 1];
   const float* row = Y + (long)c * P;
   float acc = 0.f;
-  for (int p = s + lane; p < e; p += 32) acc += fmaxf(fmaf(row[p], a, b), 0.f);
+  if (mask) {   // training-mode Dropout of the head activation (point_net.py:29-30): mask[c][p] in {0, 1/(1-p)}
+    const float* mrow = mask + (long)c * P;
+    for (int p = s + lane; p < e; p += 32) acc += fmaxf(fmaf(row[p], a, b), 0.f) * mrow[p];
+  } else {
+    for (int p = s + lane; p < e; p += 32) acc += fmaxf(fmaf(row[p], a, b), 0.f);
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) out[(long)c * ndet + d] = e > s ? acc / (float)(e - s) : 0.f;
@@ -231,9 +236,33 @@ extern "C" size_t mmmot_pointnet_workspace(int pairs, int L, long p_total) {
   return a.off;
 }
 
+extern "C" size_t mmmot_pointnet_train_workspace(int pairs, int L, long p_total) {
+  MmArena a(nullptr, 0);
+  carve(a, pairs, L, p_total, p_total / 128 + 2 * pairs + 2, false);
+  return a.off;
+}
+
+// train: FP32 engine; head_mask (optional) = the Dropout mask of the head activation, [512][P] with values {0, 1/(1-p)}
+static int pointnet_impl(const mmmot_weights* wts, const float* points, const int* det_split, const int* h_det_split,
+                         int pairs, int L, float* feats, void* workspace, size_t workspace_bytes, void* stream, bool train,
+                         const float* head_mask);
+
 extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points, const int* det_split,
                                   const int* h_det_split, int pairs, int L, float* feats,
                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return pointnet_impl(wts, points, det_split, h_det_split, pairs, L, feats, workspace, workspace_bytes, stream, false, nullptr);
+}
+
+extern "C" int mmmot_pointnet_train_fwd(const mmmot_weights* wts, const float* points, const int* det_split,
+                                        const int* h_det_split, int pairs, int L, const float* head_drop_mask, float* feats,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  return pointnet_impl(wts, points, det_split, h_det_split, pairs, L, feats, workspace, workspace_bytes, stream, true,
+                       head_drop_mask);
+}
+
+static int pointnet_impl(const mmmot_weights* wts, const float* points, const int* det_split, const int* h_det_split,
+                         int pairs, int L, float* feats, void* workspace, size_t workspace_bytes, void* stream, bool train,
+                         const float* head_mask) {
   if (!wts || !points || !det_split || !h_det_split || !feats || !workspace || pairs <= 0 || L <= 0)
     return MMMOT_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -244,7 +273,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     if (h_det_split[d + 1] <= h_det_split[d]) return MMMOT_E_SHAPE;  // every detection owns >= 1 point
 
   // column tiles never straddle two frame-pairs (one pair = one GroupNorm domain)
-  const bool use_tc = pointnet_use_tc(L);
+  const bool use_tc = !train && pointnet_use_tc(L);
   const int TNW = use_tc ? tc::BN : 128;
   long n_tiles = 0;   // the host needs only the COUNT (launch geometry); the table itself is built on the device
   for (int p = 0; p < pairs; p++) n_tiles += mm_cdiv((long)h_det_split[(p + 1) * L] - h_det_split[p * L], TNW);
@@ -427,7 +456,7 @@ extern "C" int mmmot_pointnet_fwd(const mmmot_weights* wts, const float* points,
     MM_TRY(gn_finalize(w.stats, wts->w[MMMOT_W_PN_GHW], wts->w[MMMOT_W_PN_GHB], w.cnt, 0, pairs, 512, 1,
                        w.sc, w.sh, st));
     segment_mean_kernel<<<mm_cdiv(512L * ndet * 32, 256), 256, 0, st>>>(w.big, P, det_split, w.sc, w.sh,
-                                                                        512, ndet, L, w.hmean);
+                                                                        512, ndet, L, w.hmean, head_mask);
     MM_LAUNCH_CHECK();
   }
   }

@@ -45,13 +45,17 @@ __global__ void maxpool2_nchw_kernel(const float* __restrict__ in, float* __rest
   const float* src = in + (plane * (2 * Ho) + 2 * yo) * (long)(2 * Wo) + 2 * xo;
   out[idx] = fmaxf(fmaxf(src[0], src[1]), fmaxf(src[2 * Wo], src[2 * Wo + 1]));
 }
-__global__ void plane_mean_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long planes, int hw) {
+// mask (optional): DropBlock weights [img][hw] = block_mask * numel / sum (modules/dropblock.py:49-53), applied before
+// the SkipPool head's average pool (modules/appear_net.py:27-30)
+__global__ void plane_mean_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, long planes, int hw,
+                                       const float* __restrict__ mask, int C) {
   long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= planes) return;
   const float* src = in + w * hw;
+  const float* mk = mask ? mask + (w / C) * hw : nullptr;
   float s = 0.f;
-  for (int i = lane; i < hw; i += 32) s += src[i];
+  for (int i = lane; i < hw; i += 32) s += mk ? src[i] * mk[i] : src[i];
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[w] = s / (float)hw;
@@ -99,7 +103,8 @@ extern "C" size_t mmmot_appearance_train_workspace(int n_img, int H, int W) {
 }
 
 extern "C" int mmmot_appearance_train_fwd(const mmmot_weights* wts, const float* crops, int n_img, int H, int W, int L,
-                                          float* feats, float* bn_stats, void* workspace, size_t workspace_bytes,
+                                          float* feats, float* bn_stats, const float* drop_mask2,
+                                          const float* drop_mask3, void* workspace, size_t workspace_bytes,
                                           void* stream) {
   if (!wts || !crops || !feats || !bn_stats || !workspace || n_img <= 0 || L <= 0) return MMMOT_E_ARG;
   if (H % 32 || W % 32 || H <= 0 || W <= 0 || n_img % L) return MMMOT_E_SHAPE;
@@ -142,7 +147,8 @@ extern "C" int mmmot_appearance_train_fwd(const mmmot_weights* wts, const float*
       const int s = kSkip[i];
       if (s >= 0) {
         const long planes = (long)n_img * kSkipCh[s];
-        plane_mean_nchw_kernel<<<mm_cdiv(planes * 32, 256), 256, 0, st>>>(cur, w.pooled[s], planes, h * wd);
+        const float* mask = s == 2 ? drop_mask2 : s == 3 ? drop_mask3 : nullptr;
+        plane_mean_nchw_kernel<<<mm_cdiv(planes * 32, 256), 256, 0, st>>>(cur, w.pooled[s], planes, h * wd, mask, kSkipCh[s]);
         MM_LAUNCH_CHECK();
       }
     }

@@ -322,15 +322,35 @@ class TrackingNet(nn.Module):
         mod.running_var.mul_(1 - momentum).add_(unbiased, alpha=momentum)
         mod.num_batches_tracked += 1
 
+    @staticmethod
+    def _dropblock_weights(n_img, h, w, block_size, drop_prob=0.1):
+        """DropBlock2D (reference modules/dropblock.py:28-67): Bernoulli(gamma) seeds from torch's CPU generator (the
+        reference calls torch.rand without a device and moves the mask afterwards), grown to block_size x block_size
+        blocks by a max-pool, inverted, scaled by numel / sum.  Returns the per-pixel weights n_img x h x w (CPU)."""
+        gamma = drop_prob / (block_size ** 2)
+        seeds = (torch.rand(n_img, h, w) < gamma).float()
+        grown = torch.nn.functional.max_pool2d(seeds[:, None], kernel_size=(block_size, block_size), stride=(1, 1),
+                                               padding=block_size // 2)
+        if block_size % 2 == 0:
+            grown = grown[:, :, :-1, :-1]
+        keep = 1 - grown.squeeze(1)
+        return (keep * (keep.numel() / keep.sum())).contiguous()
+
+    @staticmethod
+    def _dropout_mask(shape, dev, p=0.5):
+        """nn.Dropout(p) of the PointNet head (reference modules/point_net.py:23,29-30) as a multiplicative mask with
+        values {0, 1/(1-p)}, drawn by torch's own dropout on the activation's device, i.e. from the generator the
+        reference consumes for a tensor of this shape."""
+        return torch.nn.functional.dropout(torch.ones(shape, device=dev), p=p, training=True)
+
     @torch.no_grad()
     def _forward_train(self, dets, det_info, dets_split):
         """reference TrackingNet.forward with self.training (modules/tracking_net.py:152-162, 183-192): BatchNorm layers
         (VGG trunk, w_det) normalise with the statistics of this sample and update their running averages, det_scores are
         raw logits without the neg_threshold step, new/end scores are not zero-padded.  Forward only — no autograd graph
-        is built through the CUDA library.  DropBlock / Dropout are not implemented (the four pp_* configs switch them
-        off: dropblock 0, use_dropout False)."""
-        if self.dropblock or self.use_dropout:
-            raise NotImplementedError("mmmot_b200.TrackingNet training-mode forward: dropblock / use_dropout are not implemented")
+        is built through the CUDA library.  DropBlock (the two deepest SkipPool heads) and the PointNet head's Dropout
+        (rrc_pfv config: dropblock 5, use_dropout True) draw their masks from torch's generators exactly as the reference
+        does (_dropblock_weights / _dropout_mask) and the library applies them."""
         if len(dets_split) != 2:
             raise NotImplementedError("mmmot_b200.TrackingNet supports 2-frame samples (sample_max_len: 2)")
         n, m = int(dets_split[0]), int(dets_split[1])
@@ -352,20 +372,27 @@ class TrackingNet(nn.Module):
         end = torch.empty(1, 3, n, device=dev)
         bn_vgg = torch.zeros(13, 2, 512, device=dev)
         bn_det = torch.zeros(2, 2, 512, device=dev)
-        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        # random masks, in the reference's draw order: appearance heads 2 and 3 (CPU generator), then the PointNet head
+        dm2 = dm3 = hmask = None
+        if self.dropblock:
+            dm2 = self._dropblock_weights(L, H // 16, W // 16, int(self.dropblock)).to(dev)
+            dm3 = self._dropblock_weights(L, H // 32, W // 32, int(self.dropblock)).to(dev)
+        if self.use_dropout:
+            hmask = self._dropout_mask((512, int(split[-1])), dev).contiguous()
         with torch.cuda.device(dev):
             st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            need = max(lib.mmmot_appearance_train_workspace(L, H, W), lib.mmmot_pointnet_workspace(1, L, int(split[-1])),
+            need = max(lib.mmmot_appearance_train_workspace(L, H, W), lib.mmmot_pointnet_train_workspace(1, L, int(split[-1])),
                        lib.mmmot_fusion_det_workspace(1, L), lib.mmmot_affinity_workspace(1, n, m),
                        lib.mmmot_w_det_train_workspace(L))
             ws = self._workspace(need, dev)
             wsp, wsn = vp(ws), ctypes.c_size_t(ws.numel())
             _lib.check(lib.mmmot_status_reset(wsp, st), "mmmot_status_reset")
-            _lib.check(lib.mmmot_appearance_train_fwd(wts.ptr, vp(crops), L, H, W, L, vp(feats), vp(bn_vgg), wsp, wsn, st),
-                       "mmmot_appearance_train_fwd")
+            _lib.check(lib.mmmot_appearance_train_fwd(wts.ptr, vp(crops), L, H, W, L, vp(feats), vp(bn_vgg), vp(dm2), vp(dm3),
+                                                      wsp, wsn, st), "mmmot_appearance_train_fwd")
             hs = split.numpy()
-            _lib.check(lib.mmmot_pointnet_fwd(wts.ptr, vp(points), vp(split.to(dev)), ctypes.c_void_p(hs.ctypes.data), 1, L,
-                                              vp(feats), wsp, wsn, st), "mmmot_pointnet_fwd")
+            _lib.check(lib.mmmot_pointnet_train_fwd(wts.ptr, vp(points), vp(split.to(dev)), ctypes.c_void_p(hs.ctypes.data), 1, L,
+                                                    vp(hmask), vp(feats), wsp, wsn, st), "mmmot_pointnet_train_fwd")
             _lib.check(lib.mmmot_fusion_det_fwd(wts.ptr, _lib.FUSION[self.score_fusion_arch], 0, 0.0, 1, L, vp(feats), vp(det),
                                                 wsp, wsn, st), "mmmot_fusion_det_fwd")
             _lib.check(lib.mmmot_w_det_train_fwd(wts.ptr, L, vp(feats), vp(det), vp(bn_det), wsp, wsn, st), "mmmot_w_det_train_fwd")

@@ -174,7 +174,11 @@ def stitch_goldens():
 TRAIN_CASES = [
     ("train_mul_A_n6x5", "A", "multiply", "none", 6, 5, 24, 32, True, 21),
     ("train_subabs_dualadd_C_n7", "C", "minus_abs", "dual_add", 7, 7, 32, 32, False, 22),
+    # experiments/rrc_pfv_40e_subabs_dualadd_C/config.yaml:32-33: dropblock 5, use_dropout True (64-px crops: 4x4 and 2x2
+    # head maps, so blocks really differ per pixel); torch.manual_seed(seed) right before the forward
+    ("train_drop_subabs_dualadd_C_n9x6", "C", "minus_abs", "dual_add", 9, 6, 40, 64, True, 23),
 ]
+TRAIN_DROP = {"train_drop_subabs_dualadd_C_n9x6": dict(dropblock=5, use_dropout=True)}
 
 
 # experiments/pp_pv_40e_dualadd_subabs_C/config.yaml:39-45 through utils/build_util.py:147-155
@@ -211,11 +215,13 @@ def train_goldens():
         net = ref_loader.load_tracking_net(
             seq_len=2, score_arch="branch_cls", appear_arch="vgg", appear_len=512, appear_skippool=True, appear_fpn=False,
             point_arch="v1", point_len=512, without_reflectivity=True, softmax_mode=sm, affinity_op=op, end_arch="v2",
-            end_mode="avg", test_mode=2, score_fusion_arch=fusion, neg_threshold=0.2, dropblock=0, use_dropout=False)
+            end_mode="avg", test_mode=2, score_fusion_arch=fusion, neg_threshold=0.2,
+            **TRAIN_DROP.get(name, dict(dropblock=0, use_dropout=False)))
         sd = synthetic_state_dict(fusion, seed=seed)
         net.load_state_dict(sd, strict=True)
         net.train()
         dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
+        torch.manual_seed(seed)              # the DropBlock / Dropout draws (CPU generator) start from here
         with torch.no_grad():
             det, link, new, end, trans = net(dets, info, split)
         after = {k: v.clone() for k, v in net.state_dict().items() if "running_" in k or "num_batches" in k}
@@ -232,7 +238,7 @@ def train_goldens():
             torch.Tensor.eq = orig_eq
         out = {"case": case, "det": det, "link": link[0], "new": new, "end": end, "trans1": trans[0], "trans2": trans[1],
                "running": after, "gt_det": gt_det, "gt_link": gt_link[0], "gt_new": gt_new, "gt_end": gt_end,
-               "loss": loss.detach().clone()}
+               "loss": loss.detach().clone(), "drop": TRAIN_DROP.get(name, dict(dropblock=0, use_dropout=False))}
         torch.save(out, os.path.join(OUT, name + ".pt"))
         print(name, float(loss), tuple(det.shape), tuple(new.shape), tuple(end.shape))
 

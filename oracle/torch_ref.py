@@ -58,9 +58,23 @@ def vgg_maps(sd, dets):
     return maps
 
 
-def skip_pool(sd, s, fmap):
-    """modules/appear_net.py:27-32 with fc from :18-25 (dropblock is identity in eval)."""
+def drop_block(x, block_size, drop_prob=0.1):
+    """modules/dropblock.py:28-67 (DropBlock2D.forward in training): seeds from the CPU generator, max-pooled into
+    blocks, inverted, rescaled by numel / sum."""
+    mask = (torch.rand(x.shape[0], *x.shape[2:]) < drop_prob / (block_size ** 2)).float()
+    bm = F.max_pool2d(mask[:, None], kernel_size=(block_size, block_size), stride=(1, 1), padding=block_size // 2)
+    if block_size % 2 == 0:
+        bm = bm[:, :, :-1, :-1]
+    bm = 1 - bm.squeeze(1)
+    return x * bm[:, None] * bm.numel() / bm.sum()
+
+
+def skip_pool(sd, s, fmap, dropblock=0):
+    """modules/appear_net.py:27-32 with fc from :18-25 (dropblock is identity in eval; in training the two deepest heads
+    carry one when the config sets dropblock, appear_net.py:143-152)."""
     p = f"appearance.global_pool.{s}.fc"
+    if dropblock:
+        fmap = drop_block(fmap, dropblock)
     o = fmap.mean(dim=(2, 3), keepdim=True)
     o = group_norm(o, 1, sd[f"{p}.0.weight"], sd[f"{p}.0.bias"])
     o = F.conv2d(o, sd[f"{p}.1.weight"], sd[f"{p}.1.bias"])
@@ -127,12 +141,15 @@ def pointnet_feat(sd, x, split):
     return [local, glob], [t1, t2]
 
 
-def pointnet(sd, points_t, split):
-    """modules/point_net.py:25-44 (PointNet_v1.forward); points_t is 1 x 3 x P_t."""
+def pointnet(sd, points_t, split, dropout=False):
+    """modules/point_net.py:25-44 (PointNet_v1.forward); points_t is 1 x 3 x P_t.  dropout: the training-mode
+    nn.Dropout(0.5) of :29-30."""
     feats, trans = pointnet_feat(sd, points_t, split)
     x = torch.cat(feats, dim=1)
     x = F.conv1d(x, sd["point_net.conv1.weight"], sd["point_net.conv1.bias"])
     x = F.relu(group_norm(x, 512, sd["point_net.bn1.weight"], sd["point_net.bn1.bias"]))
+    if dropout:
+        x = F.dropout(x, p=0.5, training=True)
     seg = _segment_mean(x, split)                                   # 1 x 512 x L
     o = F.conv1d(seg, sd["point_net.conv2.weight"], sd["point_net.conv2.bias"])
     o = F.relu(group_norm(o, 16, sd["point_net.bn2.weight"], sd["point_net.bn2.bias"]))

@@ -3,8 +3,8 @@
 CPU fp32 restatement of the reference's TRAINING-mode forward and loss:
 ``TrackingNet.forward`` with ``self.training`` (modules/tracking_net.py:149-193: BatchNorm layers use batch statistics,
 det_scores stay raw logits, new/end scores are not zero-padded) and ``TrackingLoss`` (cost.py:134-185), plus the
-running-average update a training-mode BatchNorm performs.  DropBlock / Dropout are not restated (dropblock 0,
-use_dropout False: the four pp_* configs).  Pinned by tests/golden/train_*.pt, generated from the UNMODIFIED reference
+running-average update a training-mode BatchNorm performs.  DropBlock (SkipPool heads 2, 3) and the PointNet head's Dropout
+are drawn from torch's generators in the reference's order (rrc_pfv config: dropblock 5, use_dropout True).  Pinned by tests/golden/train_*.pt, generated from the UNMODIFIED reference
 in .train() mode by oracle/make_goldens.py (tests/test_oracle.py).
 """
 import torch
@@ -28,7 +28,7 @@ def _bn_train(x, sd, p, stats):
         sd[p + ".bias"].reshape(shape)
 
 
-def appearance_train(sd, dets, stats):
+def appearance_train(sd, dets, stats, dropblock=0):
     """modules/appear_net.py:166-190 with the VGG BatchNorm2d layers in training mode (modules/vgg.py:67-80)."""
     x, maps = dets, []
     for s, stage in enumerate(VGG_STAGES):
@@ -39,7 +39,8 @@ def appearance_train(sd, dets, stats):
             if idx in VGG_POOL_AFTER[s]:
                 x = F.max_pool2d(x, 2, 2)
         maps.append(x)
-    return torch.cat([torch_ref.skip_pool(sd, s, fmap) for s, fmap in enumerate(maps)], dim=-1)
+    # appear_net.py:143-152: the heads after the 4th and 5th max-pool get a DropBlock2D(block_size=dropblock)
+    return torch.cat([torch_ref.skip_pool(sd, s, fmap, dropblock if s >= 2 else 0) for s, fmap in enumerate(maps)], dim=-1)
 
 
 def determine_det_train(sd, feats, stats):
@@ -52,11 +53,13 @@ def determine_det_train(sd, feats, stats):
 
 
 @torch.no_grad()
-def forward_train(sd, dets, det_info, dets_split, fusion_arch="C", affinity_op="multiply", softmax_mode="single"):
+def forward_train(sd, dets, det_info, dets_split, fusion_arch="C", affinity_op="multiply", softmax_mode="single",
+                  dropblock=0, use_dropout=False):
     """-> (det_scores 3xL raw, [link 3xNxM], new 3xM, end 3xN, trans), bn_stats {prefix: (mean, biased var, count)}."""
     stats = {}
-    app = appearance_train(sd, dets, stats)
-    pts, trans = torch_ref.pointnet(sd, det_info["points"].transpose(-1, -2), det_info["points_split"].long().squeeze(0))
+    app = appearance_train(sd, dets, stats, dropblock)
+    pts, trans = torch_ref.pointnet(sd, det_info["points"].transpose(-1, -2), det_info["points_split"].long().squeeze(0),
+                                    dropout=use_dropout)
     feats = torch_ref.fusion(sd, fusion_arch, torch.cat([app, pts], dim=-1).t().unsqueeze(0))
     det = determine_det_train(sd, feats, stats)
     n, m = int(dets_split[0]), int(dets_split[1])

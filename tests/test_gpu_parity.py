@@ -379,13 +379,16 @@ def test_training_mode_forward_and_loss_match_reference_golden(g):
     scores, running-average update, and TrackingModule.step's loss — against the UNMODIFIED reference in .train() mode."""
     name, fusion, op, sm, n, m, pts, hw, ragged, seed = g["case"]
     net = mmmot_b200.TrackingNet(2, appear_skippool=True, score_arch="branch_cls", score_fusion_arch=fusion, affinity_op=op,
-                                 softmax_mode=sm, neg_threshold=0.2, test_mode=2, dropblock=0, use_dropout=False)
+                                 softmax_mode=sm, neg_threshold=0.2, test_mode=2, **g.get("drop", dict(dropblock=0, use_dropout=False)))
     net.load_state_dict(synthetic_state_dict(fusion, seed=seed))
     net.cuda().train()
+    # the golden ran the reference on the CPU, so its Dropout mask came from the CPU generator too: draw it there
+    net._dropout_mask = lambda shape, dev, p=0.5: torch.nn.functional.dropout(torch.ones(shape), p=p, training=True).to(dev)
     dets, info, split = synthetic_pair(n, m, pts, hw, seed=seed, ragged=ragged)
     cls, ids = synthetic_gt(n, m, seed)
     tm = mmmot_b200.TrackingModule(net, None, mmmot_b200.TrackingLoss(**LOSS_KW))
     dinfo = {k: v.cuda() for k, v in info.items()}
+    torch.manual_seed(seed)       # DropBlock / Dropout draws start where the golden's did (make_goldens.py)
     det, link, new, end, trans = net(dets.cuda(), dinfo, split)
     assert det.shape == (3, n + m) and new.shape == (3, m) and end.shape == (3, n)
     assert relerr(det, g["det"]) < TOL and relerr(link[0], g["link"]) < TOL
@@ -398,6 +401,7 @@ def test_training_mode_forward_and_loss_match_reference_golden(g):
             else:
                 assert relerr(sd_after[k], v) < 1e-4, k
     # the loss through TrackingModule.step (second training-mode forward: the outputs do not depend on running stats)
+    torch.manual_seed(seed)
     loss = tm.step(dets.cuda(), dinfo, ids, cls, split)
     assert abs(float(loss) - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
     # back to eval: the eval forward still works and pads / squashes as before
