@@ -296,7 +296,8 @@ int mmmot_set_kseg(int chunks);
  *   bit 6 (64)   64-channel layers on the channel-major kernel instead of the pixel-major one
  *   bit 7 (128)  pixel-major epilogue with 128-bit instead of 256-bit stores
  *   bit 8 (256)  pixel-major kernel without halo boxes (nine boxes per channel chunk)
- *   bit 9 (512)  no fused max-pool in the pixel-major epilogue */
+ *   bit 9 (512)  no fused max-pool in the pixel-major epilogue
+ *   bit 14 (16384) first VGG layer with a separate im2col pre-pass instead of in-kernel operand producers */
 int mmmot_set_debug(int flags);
 
 /* Test hook: Y[M][S] = W X + bias through the FP32 FFMA engine (engine must be 1); Wt is [K][M] fp32, X is [K][S],

@@ -322,6 +322,11 @@ extern "C" int mmmot_appearance_fwd(const mmmot_weights* wts, const float* crops
           conv0_packed_kernel<<<mm_cdiv(n_pix / 2, 64), 256, 0, st>>>(crops, wts->w[MMMOT_W_VGG_WT0], wts->w[MMMOT_W_VGG_B0],
                                                                      n_pix / 2, h, w, hb[which], plane_out, status);
           MM_LAUNCH_CHECK();
+        } else if (wts->w[MMMOT_W_VGG_WPX0] && !(mm_debug_flags() & 16384) && ((long)h * w) % 256 == 0 && w <= 512) {
+          // taps generated inside the contraction kernel (no im2col matrix in HBM)
+          MM_TRY(gemm_tma_px_launch_gen27(crops, n_img, h, w, (const uint4*)wts->w[MMMOT_W_VGG_WPX0],
+                                          wts->tc_scale[MMMOT_W_VGG_WP0], wts->w[MMMOT_W_VGG_B0], hb[which], plane_out,
+                                          status, st));
         } else {
           if (n_pix >= (1L << 31)) return MMMOT_E_SHAPE;
           __half* cols = hb[which ^ 1];   // [2][pixels][32] taps, dead once the contraction has run

@@ -49,6 +49,8 @@ struct TmaP {
                             // detection (g.seg[column]) into segsum[det][M] as 2^-32 fixed point (order-independent)
   int* status;              // workspace status word (FP16 range flag of the planar outputs) or null
   int wcompact;             // pixel-major kernel: t.Wp holds the compact N = 64 tiles (8 KB per k chunk, weights.py::pack_px)
+  const float* gen_src;     // pixel-major kernel, GEN27 variant: fp32 NCHW 3-channel crops [n_img][3][H][W]; the 27 (+5 zero)
+                            // taps of every pixel (k = ci*9 + ky*3 + kx) are built in shared memory by producer warps
   const int4* chunk_tab;    // matrix mode with g.seg: per (column tile, half) the four 32-column chunks' descriptors
                             // (first detection index << 1) | (chunk complete and inside ONE detection); see
                             // seg_chunk_tab_kernel.  One uniform 16-byte load per subtile instead of a load + 12 shuffles.
@@ -625,10 +627,48 @@ static inline int make_map_4d(CUtensorMap* m, const void* basep, int n_img, int 
 // pixel-major kernel for 64-channel planar outputs (see gemm_tma_px.cuh); P fully prepared by the caller
 static int gemm_tma_px_launch(tma::TmaP& P, const CUtensorMap& mh, const CUtensorMap& ml, int sms, cudaStream_t st) {
   static std::atomic<unsigned long long> attr{0};
-  MM_TRY(mm_ensure_smem(tma::gemm_tma_px_kernel, tma::PX_SMEM_BYTES, attr));
+  MM_TRY(mm_ensure_smem(tma::gemm_tma_px_kernel<false>, tma::PX_SMEM_BYTES, attr));
   const long total = P.t.g.num_tiles;
   const int grid = (int)(total < sms ? total : sms);
-  tma::gemm_tma_px_kernel<<<grid, tma::T_THREADS, tma::PX_SMEM_BYTES, st>>>(P, mh, ml);
+  tma::gemm_tma_px_kernel<false><<<grid, tma::T_THREADS, tma::PX_SMEM_BYTES, st>>>(P, mh, ml);
+  MM_LAUNCH_CHECK();
+  return 0;
+}
+
+// First VGG layer (3 -> 64 channels, 3x3 / pad 1) straight from the fp32 NCHW crops: the K = 32 operand (27 taps + 5
+// zeros per pixel, FP16 hi/lo) is generated in shared memory by the kernel's producer warps, so the im2col matrix
+// (128 B per pixel written and read back) never exists.  Output: planar FP16 NHWC, bias + ReLU applied.
+static int gemm_tma_px_launch_gen27(const float* crops, int n_img, int H, int W, const uint4* Wpx, float out_scale,
+                                    const float* bias, __half* Yhi, long y_plane, int* status, cudaStream_t st) {
+  if (!crops || !Wpx || !Yhi) return MMMOT_E_ARG;
+  const long n_pix = (long)n_img * H * W;
+  // a tile = 256 consecutive pixels of one image; staging buffer (256 + 2W + 2) x 3 floats in two 8 KB weight slots
+  if (n_pix >= (1L << 31) || ((long)H * W) % tc::BN || (tc::BN + 2 * W + 2) * 12 > 2 * tma::PX_W_SLOT) return MMMOT_E_SHAPE;
+  int sms = 0;
+  MM_TRY(mm_sm_count(&sms));
+  static std::atomic<unsigned long long> attr{0};
+  MM_TRY(mm_ensure_smem(tma::gemm_tma_px_kernel<true>, tma::PX_SMEM_BYTES, attr));
+  tma::TmaP P;
+  memset(&P, 0, sizeof(P));
+  GemmP g = gemm_defaults();
+  g.bias = bias; g.M = 64; g.K = 32; g.relu = 1;
+  g.S = (int)n_pix; g.tiles_per_group = mm_cdiv(n_pix, tc::BN); g.num_tiles = g.tiles_per_group;
+  g.Y = reinterpret_cast<float*>(Yhi); g.y_ms = 64;
+  P.t.g = g;
+  P.t.Wp = Wpx; P.wcompact = 1;
+  P.t.m_tiles = 1; P.t.k_chunks = 1; P.t.mt_per_cta = 1;
+  P.t.out_scale = out_scale;
+  P.t.out_mode = tma::OUT_PLANAR;
+  P.t.dbg = mm_debug_flags();
+  P.plane_elems = y_plane;
+  P.ksegs = 1; P.kc_per_seg = 1;
+  P.status = status;
+  P.gen_src = crops; P.n_img = n_img; P.H = H; P.W = W;
+  alignas(64) CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  const long total = g.num_tiles;
+  const int grid = (int)(total < sms ? total : sms);
+  tma::gemm_tma_px_kernel<true><<<grid, tma::PX_GEN_THREADS, tma::PX_SMEM_BYTES, st>>>(P, dummy, dummy);
   MM_LAUNCH_CHECK();
   return 0;
 }

@@ -34,7 +34,14 @@ constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) <
 // against 128 B/clk), so reading X_hi once per k-step instead of twice is what this buys.
 constexpr int PX_WC_LBO = 2048;
 
-static __global__ void __launch_bounds__(T_THREADS, 1)
+// GEN27 variant (first VGG layer): eight extra producer warps build the K = 32 activation operand of every tile — the 27
+// taps of each pixel read from the fp32 NCHW crop, zero padding at the borders, FP16 hi/lo split — directly in the
+// SWIZZLE_64B layout TMA would have written (row = pixel, 64 B per plane; 16-byte chunk c of row r lives at chunk
+// c ^ ((r >> 1) & 3)).  Four warps (one group) complete a tile's full barrier.
+constexpr int PX_GEN_WARPS = 4, PX_GEN_THREADS = T_THREADS + 2 * 32 * PX_GEN_WARPS;
+
+template <bool GEN27>
+static __global__ void __launch_bounds__(GEN27 ? PX_GEN_THREADS : T_THREADS, 1)
 gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   const GemmP& p = P.t.g;
   extern __shared__ uint8_t smem_raw[];
@@ -60,7 +67,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
   if (tid < 64) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), GEN27 ? 1 + PX_GEN_WARPS : 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; b++) {
@@ -219,6 +226,82 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
       }
     }
     __syncwarp();
+  } else if (GEN27 && warp > T_LOAD_WARP) {
+    // =============================== OPERAND PRODUCERS (first VGG layer) ===============================
+    // Two groups of four warps take alternate tiles.  A tile is 256 consecutive pixels of ONE image (H*W is a multiple of
+    // 256); the group first stages the pixels' 3-channel neighbourhood — the linear range [r0 - W - 1, r0 + 256 + W + 1)
+    // of each channel, zero outside the image — in the stage's two unused weight slots with coalesced loads, then every
+    // thread gathers the 27 taps of its two pixels from shared memory (left / right image borders by predicate).
+    const int pw = warp - (T_LOAD_WARP + 1);
+    const int grp = pw >> 2;
+    const int pt = (pw & 3) * 32 + lane;        // 0..127: rows pt and pt + 128 of the group's tiles
+    const int W = P.W, hw = P.H * P.W;
+    const int span = BN + 2 * W + 2;
+    float amax = 0.f;
+    uint32_t it = (uint32_t)grp;
+    for (long t = blockIdx.x + (long)grp * gridDim.x; t < total_tiles; t += 2L * gridDim.x, it += 2) {
+      const int s = it % STAGES;
+      const long row0 = t * BN;
+      const long img = row0 / hw;
+      const int r0 = (int)(row0 - img * hw);
+      const float* src = P.gen_src + img * 3 * hw;
+      mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+      float* stg = reinterpret_cast<float*>(sm + s * PX_STAGE + PX_W_SLOT);
+      const int lin0 = r0 - W - 1;
+#pragma unroll 1
+      for (int i0 = pt; i0 < 3 * span; i0 += 8 * 128) {
+        float q[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {           // eight independent loads in flight per thread
+          const int i = i0 + u * 128;
+          const int ci = i / span, lin = lin0 + (i - ci * span);
+          q[u] = (i < 3 * span && lin >= 0 && lin < hw) ? __ldg(src + (long)ci * hw + lin) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (i0 + u * 128 < 3 * span) stg[i0 + u * 128] = q[u];
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      const uint32_t sx = base + s * PX_STAGE + PX_X_OFF;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int rr = j * 128 + pt;
+        const int x = (r0 + rr) % W;
+        const bool xl = x > 0, xr = x < W - 1;
+        const float* c = stg + rr + W + 1;
+        float v[28];
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+              float q = c[ci * span + (ky - 1) * W + (kx - 1)];
+              if (kx == 0 && !xl) q = 0.f;
+              if (kx == 2 && !xr) q = 0.f;
+              v[ci * 9 + ky * 3 + kx] = q;
+              amax = fmaxf(amax, fabsf(q));
+            }
+        v[27] = 0.f;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int k = 0; k < 28; k += 2) split_f16x2(v[k], v[k + 1], hi[k >> 1], lo[k >> 1]);
+        hi[14] = hi[15] = lo[14] = lo[15] = 0u;
+        const uint32_t rowaddr = sx + (uint32_t)rr * 64u, sw = (uint32_t)((rr >> 1) & 3);
+#pragma unroll
+        for (int cch = 0; cch < 4; cch++) {
+          const uint32_t a = rowaddr + ((cch ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * cch]), "r"(hi[4 * cch + 1]),
+                       "r"(hi[4 * cch + 2]), "r"(hi[4 * cch + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + PX_X_PLANE), "r"(lo[4 * cch]),
+                       "r"(lo[4 * cch + 1]), "r"(lo[4 * cch + 2]), "r"(lo[4 * cch + 3]) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(s));
+    }
+    mm_range_flag(P.status, amax);
   } else {
     // =============================== LOADER ===============================
     if (lane == 0) {
@@ -230,7 +313,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
         for (int si = 0; si < nstage; si++, it++) {
           const int s = it % STAGES;
           mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(full_bar(s), (uint32_t)ntap * PX_W_SLOT + 2u * xbytes);
+          mbar_expect_tx(full_bar(s), (uint32_t)ntap * PX_W_SLOT + (GEN27 ? 0u : 2u * xbytes));
           const uint32_t sw = base + s * PX_STAGE, sx = sw + PX_X_OFF;
           const int kx = P.halo ? si / cchunks : 0, cc = P.halo ? si - kx * cchunks : 0;
           for (int ky = 0; ky < ntap; ky++) {
@@ -254,7 +337,7 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
             const int dx = tap % 3 - 1, dy = tap / 3 - 1;
             tma_load_4d(sx, &map_hi, c2 * BK, x0 + dx, y0 + dy, i0, full_bar(s));
             tma_load_4d(sx + PX_X_PLANE, &map_lo, c2 * BK, x0 + dx, y0 + dy, i0, full_bar(s));
-          } else {
+          } else if (!GEN27) {
             tma_load_2d(sx, &map_hi, si * BK, nt * BN, full_bar(s));
             tma_load_2d(sx + PX_X_PLANE, &map_lo, si * BK, nt * BN, full_bar(s));
           }
