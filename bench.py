@@ -88,7 +88,33 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
 
+    def _nvml(self):
+        """In-process NVML handle (cheap queries).  A nvidia-smi subprocess per sample re-initialises the driver every
+        time (~0.5 s each on these boxes) and was seen to stall the launching thread's CUDA calls; kept as fallback only."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
+        while not self.stop_flag and nv is not None:
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                act = lambda bit: "Active" if r & bit else "Not Active"
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                  str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), act(nv.nvmlClocksEventReasonHwSlowdown),
+                                  act(nv.nvmlClocksEventReasonHwThermalSlowdown), act(nv.nvmlClocksEventReasonSwThermalSlowdown),
+                                  act(nv.nvmlClocksEventReasonSwPowerCap)])
+            except Exception:
+                pass
+            time.sleep(0.1)
         while not self.stop_flag:
             try:
                 o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -231,7 +257,10 @@ def kernel_table(tags, steps, peaks):
         if ms <= 0:
             continue
         tf, gb = fl / ms / 1e9, by / ms / 1e6
-        bound = "latency" if name == "lp.assign" else ("tensor" if name.startswith(TENSOR_TAGS) and name != "vgg.conv0" else "hbm")
+        # vgg.pool_mean_heads: the per-image fixed-point sums it reads were written by the preceding conv epilogue's atomics
+        # and are still L2-resident (100 MB per launch in ~20 us), so an HBM fraction would be meaningless
+        bound = "latency" if name == "lp.assign" else "l2" if name == "vgg.pool_mean_heads" else \
+            ("tensor" if name.startswith(TENSOR_TAGS) and name != "vgg.conv0" else "hbm")
         row = {"kernel": name, "launches_per_step": cnt / steps, "ms_per_step": ms / steps, "bound": bound,
                "algorithmic_tflops": round(tf, 1), "algorithmic_gbs": round(gb, 1)}
         if bound == "tensor":
