@@ -316,7 +316,8 @@ extern "C" int mmmot_affinity_fwd(const mmmot_weights* wts, int affinity_op, int
   AfWs w = carve(ar, pairs, n, m);
   if (!ar.ok()) return MMMOT_E_WORKSPACE;
   const int G = pairs * 3, NM = n * m, L = n + m;
-  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && NM >= 256);   // per-pair shape only (see appearance.cu)
+  const bool use_tc = mm_engine() == 2 || (mm_engine() == 0 && NM >= 64);   // per-pair shape only (see appearance.cu); a
+  // quarter-filled 256-column tile on the tensor cores still beats the FP32 engine (N = 8: 31k -> see DESIGN §6)
   const int tpg = mm_cdiv(NM, use_tc ? tc::BN : 128);
   const float* const* W = wts->w;
   const bool timed = mm_timing_on();

@@ -248,6 +248,11 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
       mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
       float* stg = reinterpret_cast<float*>(sm + s * PX_STAGE + PX_W_SLOT);
       const int lin0 = r0 - W - 1;
+      if (P.t.dbg & 4) {                         // A/B: no operand generation (results wrong)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
+        continue;
+      }
 #pragma unroll 1
       for (int i0 = pt; i0 < 3 * span; i0 += 8 * 128) {
         float q[8];

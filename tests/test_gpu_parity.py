@@ -206,6 +206,41 @@ def test_batched_equals_looped():
         assert torch.equal(o["new"][b], new[:, n:]) and torch.equal(o["end"][b], end[:, :n])
 
 
+def test_host_pipeline_equals_predict_batch():
+    """HostPipeline (pinned host -> overlapped H2D -> predict_batch per sub-batch -> D2H; what bench.py times as e2e)
+    returns exactly what predict_batch returns on device-resident inputs, on ragged point counts, across repeated runs
+    (buffer / pinned-slot reuse) and for a batch that cannot be cut into sub-batches."""
+    net, sd = make_net("C", "minus_abs", "dual_add", 0.2, 5)
+    n = 8
+    for B, seed in ((8, 50), (3, 60)):
+        ds, ps, sp, off = [], [], [torch.zeros(1, dtype=torch.int64)], 0
+        for b in range(B):
+            d, info, _ = synthetic_pair(n, n, 24, 32, seed=seed + b, ragged=True)
+            ds.append(d); ps.append(info["points"][0])
+            s_ = info["points_split"][0].long()
+            sp.append(s_[1:] + off); off += int(s_[-1])
+        crops, pts, split = torch.cat(ds), torch.cat(ps), torch.cat(sp)
+        ref = net.predict_batch(crops.cuda(), pts.cuda(), split, n)
+        pipe = mmmot_b200.HostPipeline(net, n, sub_batches=4)
+        h_crops, h_pts = crops.pin_memory(), pts.pin_memory()
+        for _ in range(3):
+            r = pipe.run(h_crops, h_pts, split)
+            assert torch.equal(r["match"], ref["match"].cpu()) and torch.equal(r["match_device"], ref["match"])
+            for k in ("assign_det", "assign_new", "assign_end"):
+                assert torch.equal(r[k], ref[k].cpu()), k
+        assert pipe.nsub == (4 if B == 8 else 1)
+        h2d, d2h = pipe.bytes_per_batch(h_crops, h_pts, split)
+        assert h2d == crops.numel() * 4 + pts.numel() * 4 + split.numel() * 4 and d2h > 0
+    # the range flag travels through the pipeline too
+    from mmmot_b200 import _lib
+    mmmot_b200.set_engine("tcgen05")
+    try:
+        with pytest.raises(_lib.MmmotError, match="MMMOT_E_RANGE"):
+            pipe.run((h_crops * 1e6).pin_memory(), h_pts, split)
+    finally:
+        mmmot_b200.set_engine("auto")
+
+
 # ------------------------------------------------------------------ LP
 def _rand_lp(g, n, m, B=1):
     L = n + m
