@@ -160,7 +160,40 @@ gemm_tma_px_kernel(const TmaP P, const __grid_constant__ CUtensorMap map_hi, con
           split_f16x2(x0v, x1v, hi[j >> 1], lo[j >> 1]);
           mm_range_track2(racc, hi[j >> 1]);
         }
-        if (ok && !(P.t.dbg & 128)) {
+        if (GEN27) {
+          // Line-coalesced stores.  A thread owns 64 B per plane of ONE pixel, so a warp-wide store of it touches 32
+          // different 128-byte lines (32 LSU wavefronts per instruction; this epilogue is what bounds the layer).  The
+          // two warps of a TMEM lane quadrant (channel halves 0-31 / 32-63 of the same 32 pixels) exchange through an
+          // 8 KB scratch [plane][pixel][128 B] (16-byte chunk c of pixel p at slot c ^ (p & 7): conflict-free both ways)
+          // in an unused tail of the stage buffers; then one warp stores the hi plane, the other the lo plane, every
+          // instruction writing 8 complete lines.
+          const uint32_t scr = base + (uint32_t)((q >> 1) * PX_STAGE + PX_X_OFF + (q & 1) * PX_X_PLANE + 16384);
+          const uint32_t rowa = scr + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t slot = (uint32_t)((((cb >> 3) + k) ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + slot), "r"(hi[4 * k]), "r"(hi[4 * k + 1]),
+                         "r"(hi[4 * k + 2]), "r"(hi[4 * k + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + 4096u + slot), "r"(lo[4 * k]),
+                         "r"(lo[4 * k + 1]), "r"(lo[4 * k + 2]), "r"(lo[4 * k + 3]) : "memory");
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(3 + q) : "memory");
+          const int h = warp >> 2;                                   // plane this warp stores
+          const long row0 = (long)nt * BN + sub * 128 + q * 32;
+          __half* dstp = yh + (long)h * P.plane_elems + row0 * 64;
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const int idx = r * 32 + lane, px = idx >> 2, c = (idx & 3) * 2;
+            const uint32_t ra = scr + (uint32_t)h * 4096u + (uint32_t)px * 128u;
+            uint32_t w[8];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                         : "r"(ra + (uint32_t)((c ^ (px & 7)) << 4)));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "r"(ra + (uint32_t)(((c + 1) ^ (px & 7)) << 4)));
+            if (row0 + px < p.S) st_global_256(dstp + (long)px * 64 + c * 8, w);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(3 + q) : "memory");   // scratch free for the next subtile
+        } else if (ok && !(P.t.dbg & 128)) {
           // 256-bit stores: every instruction writes whole 32-byte sectors (two per plane per thread)
           st_global_256(yh + o, hi);
           st_global_256(yh + o + 16, hi + 8);
