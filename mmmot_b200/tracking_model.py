@@ -132,6 +132,8 @@ class TrackingModule(object):
                                       else assign_link[i - 1][0]) == 1          # [prev][cur]
                     col = link[:counts[i - 1], linked]
                     if not col.any(axis=0).all():
+                        # the reference appends no id for such a detection and then trips its own
+                        # `assert len(fake_id) == det_curr_num` (tracking_model.py:281): same exception type here
                         raise AssertionError("kept detection is neither new nor linked to the previous frame")
                     local[linked] = prev_local[col.argmax(axis=0)]               # first linked previous detection
             k = int(fresh.sum())
