@@ -136,3 +136,19 @@ def test_train_oracle_matches_reference_golden(g):
     kw = {k: LOSS_KW[k] for k in ("det_ratio", "trans_ratio", "trans_last")}
     assert abs(float(train_ref.tracking_loss(*args, **kw)) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
     assert abs(float(tm.criterion(*args)) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+
+
+def test_dropblock_weights_match_oracle_dropblock():
+    """The host-side DropBlock mask generator of the product (TrackingNet._dropblock_weights) draws the same Bernoulli
+    seeds and builds the same block weights as the oracle's restatement of modules/dropblock.py (itself pinned by the
+    train_drop golden), for odd and even block sizes and 1x1 maps."""
+    import mmmot_b200
+    from oracle import torch_ref
+    for (n, h, w, bs) in ((5, 4, 4, 5), (3, 14, 14, 5), (7, 7, 7, 4), (2, 1, 1, 5)):
+        x = torch.rand(n, 6, h, w, generator=torch.Generator().manual_seed(n * 100 + h))
+        torch.manual_seed(900 + h)
+        ref = torch_ref.drop_block(x, bs)
+        torch.manual_seed(900 + h)
+        wts = mmmot_b200.TrackingNet._dropblock_weights(n, h, w, bs)
+        assert wts.shape == (n, h, w)
+        assert torch.allclose(x * wts[:, None], ref, rtol=1e-6, atol=0)
