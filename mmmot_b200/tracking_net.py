@@ -130,6 +130,9 @@ class TrackingNet(nn.Module):
         n = s_host.numel()
         ring = getattr(self, "_pin_ring", None)
         if ring is None or ring[0][0].numel() < n:
+            for old in ring or []:              # a fetch kernel may still be reading the old (smaller) pinned buffers
+                if old[1] is not None:
+                    old[1].synchronize()
             cap = max(n, 1024)
             ring = self._pin_ring = [[torch.empty(cap, dtype=torch.int32, pin_memory=True), None] for _ in range(4)]
             self._pin_next = 0
