@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) lp_assign_kernel(
       j0 = bj;
       if (p[j0] == 0) break;
     }
+    // every lane has read p[j0] before lane 0 rewrites p[] below (racecheck: read at the loop exit vs the augmenting write)
+    __syncwarp();
     // augment along the alternating path (serial, short)
     if (lane == 0) {
       int j = j0;
